@@ -1,0 +1,97 @@
+// Host-side (cold) setup for the B200 V-cycle path: CSC container, the
+// reference's interpolation operators and Galerkin coarse operators, greedy
+// colouring, banded LDL^T of the coarsest operator, Gauss-Seidel dependency
+// schedules and the SELL-32 device layout.  Pure C++17, no CUDA, no Eigen.
+//
+// Reference behaviour restated here (paths relative to the reference root):
+//   include/amg/interpolator.hpp:106-141  LinearInterpolator::make_operators
+//   include/amg/multigrid.hpp:127-130     n_H_dofs_from_n_h_dofs
+//   include/amg/multigrid.hpp:211-237     hierarchy loop, A_H = R*(A*P)
+//   include/amg/multigrid.hpp:240-243     coarsest factorisation
+//   include/amg/grid.hpp:31-140           problem generators
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace amgb {
+
+struct Csc {
+  int rows = 0, cols = 0;
+  std::vector<int> colptr;  // cols + 1
+  std::vector<int> rowidx;  // ascending inside each column
+  std::vector<double> val;
+  int64_t nnz() const { return colptr.empty() ? 0 : colptr.back(); }
+  int64_t nnz_nonzero() const;
+};
+
+Csc csc_from_arrays(int rows, int cols, const int* colptr, const int* rowidx, const double* val);
+Csc transpose(const Csc& A);
+bool bitwise_equal(const Csc& A, const Csc& B);
+
+// ---- generators (grid.hpp) ----
+double grid_spacing_h(int64_t n);
+Csc grid_laplacian(int64_t n, double eps_y);
+void grid_rhs(int64_t n, double* b);
+
+// ---- interpolation + Galerkin ----
+int64_t coarse_dofs(int64_t fine_dofs);
+Csc make_prolongation(int64_t n_h, int64_t n_H);
+// Eigen 3.4.0 conservative ColMajor product: entry (i,j) = sum over ascending k
+// of L(i,k)*R(k,j); numerical zeros kept; result columns sorted.
+Csc multiply(const Csc& L, const Csc& R);
+Csc galerkin(const Csc& R, const Csc& A, const Csc& P);
+
+// ---- greedy first-fit colouring of the (pruned, symmetrised) graph ----
+int greedy_coloring(const Csc& A, const Csc& AT, std::vector<int>& color);
+
+// ---- coarsest level: banded LDL^T, natural order, no pivoting ----
+struct BandedLdlt {
+  int n = 0, bw = 0;
+  std::vector<double> L;  // n * max(bw,1): L[i*bw + (j-(i-bw))] = L(i,j), i-bw <= j < i
+  std::vector<double> d;  // n
+};
+BandedLdlt factor_banded_ldlt(const Csc& A);
+
+// ---- SELL-32 layout of "row c = CSC column c", explicit zeros dropped ----
+// Slice s holds rows [32 s, 32 s + 32) of `rows` (or of 0..n-1 when rows is
+// empty); element j of lane t sits at slice_ptr[s] + 32 j + t.  Padding has
+// col = -1.  Entries keep their ascending column order, so a thread that walks
+// j = 0.. reproduces the reference's summation order.
+struct Sell {
+  int n_rows = 0;    // rows covered (== rows.size() when a subset)
+  int n_slices = 0;
+  int64_t nnz = 0;   // real entries
+  std::vector<uint32_t> slice_ptr;  // n_slices + 1
+  std::vector<int> col;
+  std::vector<double> val;
+  std::vector<int> rows;  // optional row subset (ascending), empty = identity
+};
+Sell build_sell(const Csc& M, const std::vector<int>* rows = nullptr);
+
+// ---- Gauss-Seidel wavefront schedule on the pruned dependency DAG ----
+// forward: row k depends on rows j<k with M(j,k) != 0 (column k of M used as
+// row k); backward: rows j>k.  order lists rows grouped by wavefront.
+struct Schedule {
+  std::vector<int> order;      // n
+  std::vector<int> front_ptr;  // n_fronts + 1
+  int n_fronts() const { return (int)front_ptr.size() - 1; }
+  int max_width = 0;
+};
+Schedule gs_schedule(const Csc& M, bool forward);
+
+// ---- banded-stencil structure of an operator (for the systolic GS kernel) ----
+// Offsets d = row - col of non-zero entries, split into "near" (|d| <= q) and
+// one "far" cluster [far_lo, far_hi] (by symmetry also the negative one).
+struct BandStructure {
+  bool ok = false;
+  int near = 0;              // max |d| of the near cluster (0 = diagonal only)
+  int far_lo = 0, far_hi = 0;  // far cluster, 0/0 when absent
+  double rho_lower = 0.0;    // max_k sum_{j<k} |a_kj| / |a_kk|
+  double rho_upper = 0.0;
+  double alpha_near = 0.0;   // max_k sum_{0<k-j<=near} |a_kj| / |a_kk|
+  std::string why;           // reason when !ok
+};
+BandStructure analyze_band(const Csc& M);
+
+}  // namespace amgb

@@ -1,0 +1,291 @@
+// Device kernels of the V-cycle path (sm_100a).  All of them are HBM-bound
+// streaming kernels over the SELL-32 mirror (host_setup.hpp): one thread per
+// matrix row, a warp per 32-row slice, so every load of col/val is a full
+// 128/256-byte coalesced request and, for the banded operators of this path,
+// so are the gathers of x.  Each thread walks its row in ascending column
+// order with explicit __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn (never contracted
+// into FMAs), which reproduces the reference's summation order bit for bit:
+//   Gauss-Seidel update   include/amg/smoother.hpp:101-138
+//   residual r = f - A u  include/amg/multigrid.hpp:272-274 (Eigen: r=f; r-=A*u)
+//   restriction           include/amg/interpolator.hpp:64-68
+//   prolongation + add    include/amg/interpolator.hpp:52-56, multigrid.hpp:294-296
+//   rss                   include/amg/common.hpp:17-27
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace amgb {
+namespace dev {
+
+struct SellView {
+  int n_rows;                 // rows covered by this view
+  int n_slices;
+  const uint32_t* slice_ptr;  // n_slices + 1
+  const int* col;             // -1 = padding
+  const double* val;
+  const int* rows;            // row ids when the view is a subset, else nullptr
+};
+
+// Visit the entries of SELL row t in ascending column order.  Loads are
+// batched four at a time (4 col + 4 val loads in flight, then 4 gathers).
+template <class Fn>
+__device__ __forceinline__ void for_each_entry(const SellView& S, int t, const double* x, Fn&& fn) {
+  const int s = t >> 5;
+  const uint32_t begin = S.slice_ptr[s] + (t & 31);
+  const uint32_t end = S.slice_ptr[s + 1];
+  for (uint32_t p = begin; p < end; p += 128) {
+    int c[4];
+    double v[4], xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t q = p + 32u * k;
+      c[k] = (q < end) ? S.col[q] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t q = p + 32u * k;
+      v[k] = (c[k] >= 0) ? S.val[q] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xv[k] = (c[k] >= 0) ? x[c[k]] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (c[k] >= 0) fn(c[k], v[k], xv[k]);
+  }
+}
+
+// ((f - a1 x1) - a2 x2) - ...   (multigrid.hpp:272-274)
+__device__ __forceinline__ double row_residual(const SellView& S, int t, const double* x, double f) {
+  double acc = f;
+  for_each_entry(S, t, x, [&](int, double a, double xv) { acc = __dsub_rn(acc, __dmul_rn(a, xv)); });
+  return acc;
+}
+
+// The reference's Gauss-Seidel row update (smoother.hpp:101-138): rsum from +0,
+// off-diagonal terms added in ascending order, (b - rsum) / diag, skipped when
+// the diagonal is zero or absent.
+__device__ __forceinline__ double row_gs(const SellView& S, int t, int row, const double* x, double b,
+                                         double keep) {
+  double rsum = 0.0, diag = 0.0;
+  for_each_entry(S, t, x, [&](int c, double a, double xv) {
+    if (c == row) diag = a;
+    else rsum = __dadd_rn(rsum, __dmul_rn(a, xv));
+  });
+  return (diag == 0.0) ? keep : __ddiv_rn(__dsub_rn(b, rsum), diag);
+}
+
+// ------------------------------------------------------------------ residual
+__global__ void __launch_bounds__(256) k_residual(SellView A, const double* __restrict__ u,
+                                                  const double* __restrict__ f, double* __restrict__ r) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_rows) return;
+  r[t] = row_residual(A, t, u, f[t]);
+}
+
+// ------------------------------------------------------------------ damped Jacobi
+// u_new[k] = u[k] + omega * (r_k / a_kk), r_k as in k_residual.
+__global__ void __launch_bounds__(256) k_jacobi(SellView A, const double* __restrict__ u,
+                                                const double* __restrict__ f, double omega,
+                                                double* __restrict__ u_new) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_rows) return;
+  double acc = f[t], diag = 0.0;
+  for_each_entry(A, t, u, [&](int c, double a, double xv) {
+    if (c == t) diag = a;
+    acc = __dsub_rn(acc, __dmul_rn(a, xv));
+  });
+  const double ut = u[t];
+  u_new[t] = (diag == 0.0) ? ut : __dadd_rn(ut, __dmul_rn(omega, __ddiv_rn(acc, diag)));
+}
+
+// ------------------------------------------------------------------ multicolour GS
+// One colour: the view lists the rows of that colour; they only read other colours.
+__global__ void __launch_bounds__(256) k_color_gs(SellView C, const double* __restrict__ f, double* u) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= C.n_rows) return;
+  const int row = C.rows[t];
+  u[row] = row_gs(C, t, row, u, f[row], u[row]);
+}
+
+// ------------------------------------------------------------------ level-scheduled GS
+// Generic, bit-exact lexicographic Gauss-Seidel for any matrix: the rows of one
+// wavefront of the (zero-pruned) dependency DAG are independent; fronts run in
+// order inside ONE block (block barrier between fronts).  This is the fallback
+// for operators the systolic kernel does not cover; it is latency-bound.
+__global__ void __launch_bounds__(1024) k_gs_fronts(SellView A, const int* __restrict__ order,
+                                                    const int* __restrict__ front_ptr, int n_fronts,
+                                                    const double* __restrict__ f, double* u) {
+  for (int fr = 0; fr < n_fronts; ++fr) {
+    const int b = front_ptr[fr], e = front_ptr[fr + 1];
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const int row = order[i];
+      const int s = row >> 5;
+      const uint32_t begin = A.slice_ptr[s] + (row & 31), end = A.slice_ptr[s + 1];
+      double rsum = 0.0, diag = 0.0;
+      for (uint32_t p = begin; p < end; p += 32) {
+        const int c = A.col[p];
+        if (c < 0) break;
+        const double a = A.val[p];
+        if (c == row) diag = a;
+        else rsum = __dadd_rn(rsum, __dmul_rn(a, __ldcg(u + c)));
+      }
+      if (diag != 0.0) __stcg(u + row, __ddiv_rn(__dsub_rn(f[row], rsum), diag));
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ fused residual + restriction
+// f_c[J] = ((0 + .5 r[2J]) + 1 r[2J+1]) + .5 r[2J+2]  with r = f - A u never
+// written to HBM; also zeroes the coarse solution (multigrid.hpp:272-282).
+// A block owns 256 fine rows and the 128 coarse rows centred in them; the one
+// extra fine row 2J+2 of its last coarse row is recomputed by thread 0.
+__global__ void __launch_bounds__(256) k_residual_restrict(SellView A, const double* __restrict__ u,
+                                                           const double* __restrict__ f,
+                                                           double* __restrict__ f_coarse,
+                                                           double* __restrict__ u_coarse, int n_coarse) {
+  __shared__ double r[257];
+  const int base = blockIdx.x * 256;
+  const int t = threadIdx.x;
+  const int row = base + t;
+  r[t] = (row < A.n_rows) ? row_residual(A, row, u, f[row]) : 0.0;
+  if (t == 0) {
+    const int extra = base + 256;
+    r[256] = (extra < A.n_rows) ? row_residual(A, extra, u, f[extra]) : 0.0;
+  }
+  __syncthreads();
+  if (t < 128) {
+    const int J = (base >> 1) + t;
+    if (J < n_coarse) {
+      const double a = __dmul_rn(0.5, r[2 * t]);
+      const double b = __dadd_rn(a, r[2 * t + 1]);
+      f_coarse[J] = __dadd_rn(b, __dmul_rn(0.5, r[2 * t + 2]));
+      u_coarse[J] = 0.0;
+    }
+  }
+}
+
+// stand-alone restriction (interpolator.hpp:64-68), for the per-operator API
+__global__ void __launch_bounds__(256) k_restrict(const double* __restrict__ r, int n_fine,
+                                                  double* __restrict__ f_coarse, int n_coarse) {
+  const int J = blockIdx.x * blockDim.x + threadIdx.x;
+  if (J >= n_coarse) return;
+  double acc = 0.0;
+  const int i = 2 * J;
+  if (i < n_fine) acc = __dadd_rn(acc, __dmul_rn(0.5, r[i]));
+  if (i + 1 < n_fine) acc = __dadd_rn(acc, __dmul_rn(1.0, r[i + 1]));
+  if (i + 2 < n_fine) acc = __dadd_rn(acc, __dmul_rn(0.5, r[i + 2]));
+  f_coarse[J] = acc;
+}
+
+// ------------------------------------------------------------------ prolongation + correction add
+// u[i] = u[i] + (P e)[i]; (P e)[2J+1] = 0 + 1 e[J]; (P e)[2J] = (0 + .5 e[J-1]) + .5 e[J]
+// with the terms whose coarse index is outside [0, n_coarse) absent
+// (interpolator.hpp:52-56,118-125; multigrid.hpp:294-296).
+__device__ __forceinline__ double prolong_at(const double* __restrict__ e, int n_coarse, int i) {
+  double acc = 0.0;
+  if (i & 1) {
+    const int J = i >> 1;
+    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(1.0, e[J]));
+  } else {
+    const int J = i >> 1;
+    if (J - 1 >= 0 && J - 1 < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - 1]));
+    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J]));
+  }
+  return acc;
+}
+__global__ void __launch_bounds__(256) k_prolong_add(const double* __restrict__ e, int n_coarse,
+                                                     double* __restrict__ u, int n_fine) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_fine) return;
+  u[i] = __dadd_rn(u[i], prolong_at(e, n_coarse, i));
+}
+
+// ------------------------------------------------------------------ rss = sum (b - A u)^2
+// bhat_i accumulates from +0 in ascending column order, d = b_i - bhat_i
+// (common.hpp:21-25).  The outer sum is a fixed-shape tree (deterministic; it
+// differs from the reference's sequential sum only by rounding).
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x < 32) {
+    tot = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+  }
+  return tot;  // valid in thread 0
+}
+__global__ void __launch_bounds__(256) k_rss_partial(SellView A, const double* __restrict__ u,
+                                                     const double* __restrict__ b,
+                                                     double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double sq = 0.0;
+  if (t < A.n_rows) {
+    double bhat = 0.0;
+    for_each_entry(A, t, u, [&](int, double a, double xv) { bhat = __dadd_rn(bhat, __dmul_rn(a, xv)); });
+    const double d = __dsub_rn(b[t], bhat);
+    sq = __dmul_rn(d, d);
+  }
+  const double tot = block_sum_256(sq, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partial, int n,
+                                                      double* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  const double tot = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) *out = tot;
+}
+// sum of squares of a vector (for the relative-residual criterion)
+__global__ void __launch_bounds__(256) k_sumsq_partial(const double* __restrict__ x, int n,
+                                                       double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const double v = (t < n) ? x[t] : 0.0;
+  const double tot = block_sum_256(v * v, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------ coarsest solve
+// x = (L D L^T)^{-1} f with the banded factor of host_setup.hpp, right-looking
+// substitutions (multigrid.hpp:287-288).  One block; the vector lives in shared
+// memory when it fits, else in global memory.  The per-entry update order is
+// fixed (ascending pivot in the forward pass, descending in the backward pass).
+__global__ void __launch_bounds__(1024) k_banded_ldlt_solve(const double* __restrict__ L,
+                                                            const double* __restrict__ d, int n, int bw,
+                                                            const double* __restrict__ f,
+                                                            double* __restrict__ x_out, double* work,
+                                                            int use_smem) {
+  extern __shared__ double sx[];
+  double* x = use_smem ? sx : work;
+  const int ld = bw > 0 ? bw : 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = f[i];
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    const double xi = x[i];
+    for (int t = 1 + threadIdx.x; t <= bw; t += blockDim.x) {
+      const int r = i + t;
+      if (r < n) x[r] = __dsub_rn(x[r], __dmul_rn(L[(size_t)r * ld + (i - (r - bw))], xi));
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = __ddiv_rn(x[i], d[i]);
+  __syncthreads();
+  for (int i = n - 1; i >= 0; --i) {
+    const double xi = x[i];
+    for (int t = 1 + threadIdx.x; t <= bw; t += blockDim.x) {
+      const int c = i - t;
+      if (c >= 0) x[c] = __dsub_rn(x[c], __dmul_rn(L[(size_t)i * ld + (c - (i - bw))], xi));
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) x_out[i] = x[i];
+}
+
+}  // namespace dev
+}  // namespace amgb

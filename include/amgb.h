@@ -1,0 +1,221 @@
+/*
+ * amgb.h -- C ABI of the B200-native multigrid V-cycle path (libamgb.so).
+ *
+ * This is the drop-in boundary for the hot path of jfdev001/algebraic-multigrid
+ * (reference paths below are relative to the reference repository root).
+ * Host code (the C++ headers under include/amg/, or any FFI) hands the raw
+ * CSC arrays of an Eigen::SparseMatrix<double> (outerIndexPtr / innerIndexPtr /
+ * valuePtr of a compressed ColMajor matrix, int32 indices) and plain double
+ * vectors to these entry points.  Every pointer argument is a HOST pointer
+ * unless its name ends in _dev.  No C++ / torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success or an AMGB_E* code; the message is
+ *     available from amgb_last_error() (thread-local).
+ *   - handles are opaque and own their device memory; host arrays are only
+ *     borrowed for the duration of the call.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with AMGB_ECUDA.
+ *   - the matrix mirror reads CSC column c as "row c" exactly like the
+ *     reference's Gauss-Seidel (include/amg/smoother.hpp:101-117).  For
+ *     operations defined on the rows of A (residual, Jacobi, multicolour GS)
+ *     the mirror is shared when A is bitwise symmetric and a transposed mirror
+ *     is built otherwise, so results never depend on the symmetry assumption.
+ */
+#ifndef AMGB_H_
+#define AMGB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMGB_OK 0
+#define AMGB_EINVAL 1   /* invalid argument (maps to std::invalid_argument) */
+#define AMGB_ECUDA 2    /* CUDA runtime / driver failure, or no device       */
+#define AMGB_ENCCL 3    /* NCCL failure                                       */
+#define AMGB_ESTATE 4   /* call not valid in the handle's current state       */
+
+/* Smoother kinds.  GS is the reference's smoother; the other two are the
+ * partitionable smoothers the north star adds (no reference counterpart). */
+#define AMGB_SMOOTHER_GS 0        /* include/amg/smoother.hpp:86-216 */
+#define AMGB_SMOOTHER_JACOBI 1    /* u <- u + omega D^-1 (f - A u)            */
+#define AMGB_SMOOTHER_COLOR_GS 2  /* greedy multicolour (red-black on level 0) */
+
+/* How amgb_smooth_gs orders its updates. */
+#define AMGB_GS_AUTO 0      /* fastest kernel that reproduces lexicographic order */
+#define AMGB_GS_LEVELSCHED 1 /* generic level-scheduled kernel (bit-exact)        */
+
+typedef struct amgb_matrix amgb_matrix;       /* device mirror of one CSC matrix */
+typedef struct amgb_hierarchy amgb_hierarchy; /* device mirror of AMG::Multigrid  */
+
+const char* amgb_last_error(void);
+int amgb_version(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int amgb_device_count(void);
+/* selects the device this thread's subsequent calls use (cudaSetDevice) */
+int amgb_set_device(int device);
+
+/* ------------------------------------------------------------------------
+ * Input generators -- host only, no device needed.
+ * Replace AMG::Grid<double> (include/amg/grid.hpp:19-141).
+ * ---------------------------------------------------------------------- */
+/* grid.hpp:31 */
+double amgb_grid_spacing_h(int64_t n);
+/* grid.hpp:39-41 */
+int64_t amgb_points_n_from_grid_spacing_h(double h);
+/* nnz of the n*n x n*n five-point operator: 5n^2 - 4n */
+int64_t amgb_grid_laplacian_nnz(int64_t n);
+/* grid.hpp:88-98 with eps_y == 1.0; eps_y scales the kron(D,I) (+-n) coupling.
+ * colptr has n*n+1 entries, rowidx/val amgb_grid_laplacian_nnz(n). */
+int amgb_grid_laplacian(int64_t n, double eps_y, int* colptr, int* rowidx, double* val);
+/* grid.hpp:108-140 with the default f(x,y) = 5 exp(-10 (x^2+y^2)); b has n*n entries */
+int amgb_grid_rhs(int64_t n, double* b);
+
+/* ------------------------------------------------------------------------
+ * Setup helpers -- host only.  Replace LinearInterpolator::make_operators
+ * (include/amg/interpolator.hpp:106-141) and Multigrid's level-size rule
+ * (include/amg/multigrid.hpp:127-130).  Integer outputs are bit-exact.
+ * ---------------------------------------------------------------------- */
+int64_t amgb_n_H_dofs_from_n_h_dofs(int64_t n_h_dofs);
+/* number of stored entries of P for (n_h, n_H) */
+int64_t amgb_interp_nnz(int64_t n_h, int64_t n_H);
+/* P is n_h x n_H (colptr: n_H+1), R = P^T is n_H x n_h (colptr: n_h+1) */
+int amgb_interp_make_operators(int64_t n_h, int64_t n_H,
+                               int* P_colptr, int* P_rowidx, double* P_val,
+                               int* R_colptr, int* R_rowidx, double* R_val);
+
+/* ------------------------------------------------------------------------
+ * Matrix mirror + stand-alone operators (the SmootherBase::smooth boundary,
+ * include/amg/smoother.hpp:63-65).  u is updated in place.
+ * ---------------------------------------------------------------------- */
+int amgb_matrix_create(int n_rows, int n_cols, const int* colptr, const int* rowidx,
+                       const double* val, amgb_matrix** out);
+int amgb_matrix_destroy(amgb_matrix* A);
+/* stored entries after dropping explicit zeros (what the kernels stream) */
+int64_t amgb_matrix_nnz_device(const amgb_matrix* A);
+int amgb_matrix_is_symmetric(const amgb_matrix* A);
+
+/* SparseGaussSeidel::smooth (smoother.hpp:189-215): n_iters x (forward then
+ * backward lexicographic sweep); if every != 0 the residual sum of squares is
+ * evaluated every `every` iterations and the loop stops once it is <= tolerance.
+ * iters_done / final_error may be NULL (final_error is 100 if never evaluated). */
+int amgb_smooth_gs(amgb_matrix* A, double* u, const double* b, double tolerance,
+                   int64_t every, int64_t n_iters, int mode,
+                   int64_t* iters_done, double* final_error);
+/* n_sweeps damped-Jacobi sweeps */
+int amgb_smooth_jacobi(amgb_matrix* A, double* u, const double* b, double omega,
+                       int64_t n_sweeps);
+/* n_iters x (colours 0..C-1 then C-1..0) */
+int amgb_smooth_color_gs(amgb_matrix* A, double* u, const double* b, int64_t n_iters);
+/* greedy colouring used by amgb_smooth_color_gs; color has n entries */
+int amgb_matrix_coloring(amgb_matrix* A, int* n_colors, int* color);
+/* r = f - A u, in Eigen's order (include/amg/multigrid.hpp:272-274) */
+int amgb_residual(amgb_matrix* A, const double* u, const double* f, double* r);
+/* sum_i (b_i - (A u)_i)^2 (include/amg/common.hpp:17-27) */
+int amgb_rss(amgb_matrix* A, const double* u, const double* b, double* out);
+
+/* ------------------------------------------------------------------------
+ * Hierarchy = AMG::Multigrid<double> (include/amg/multigrid.hpp:22-365).
+ * ---------------------------------------------------------------------- */
+typedef struct amgb_options {
+  int n_levels;             /* multigrid.hpp:155                                   */
+  double tolerance;         /* :155  stop when sum r^2 <= tolerance                */
+  int64_t compute_error_every_n_iters; /* :155                                     */
+  int64_t n_iters;          /* :156  V-cycle cap                                   */
+  int smoother;             /* AMGB_SMOOTHER_*                                     */
+  int64_t smoother_iters;   /* SmootherBase::n_iters: GS / colour-GS symmetric
+                               sweeps, or Jacobi sweeps, per smooth() call         */
+  double omega;             /* Jacobi damping                                      */
+  int gs_mode;              /* AMGB_GS_*                                           */
+  int use_graph;            /* 1: replay the V-cycle as a CUDA graph               */
+  int skip_dead_coarse_smooth; /* 1: drop the pre-smooth + residual the reference
+                               does on the coarsest level and then overwrites
+                               (multigrid.hpp:265-274 vs :287-288); unobservable   */
+} amgb_options;
+void amgb_options_default(amgb_options* opt);
+
+/* Multigrid constructor (multigrid.hpp:151-244).  Validation order and the two
+ * AMGB_EINVAL conditions are the reference's (:165-178). */
+int amgb_hierarchy_create(int n_rows, int n_cols, const int* colptr, const int* rowidx,
+                          const double* val, const double* b, int64_t b_rows,
+                          const amgb_options* opt, amgb_hierarchy** out);
+int amgb_hierarchy_destroy(amgb_hierarchy* h);
+
+/* make the handle launch on a caller-owned cudaStream_t (NULL = its own stream) */
+int amgb_hierarchy_set_stream(amgb_hierarchy* h, void* cuda_stream);
+
+/* getters (multigrid.hpp:339-354) */
+int amgb_hierarchy_n_levels(const amgb_hierarchy* h);
+int64_t amgb_hierarchy_n_dofs(const amgb_hierarchy* h, int level);
+int64_t amgb_hierarchy_nnz(const amgb_hierarchy* h, int level);        /* structural (Eigen) */
+int64_t amgb_hierarchy_nnz_device(const amgb_hierarchy* h, int level); /* streamed by kernels */
+double amgb_hierarchy_tolerance(const amgb_hierarchy* h);
+/* host copy of level matrix (structural CSC incl. explicit zeros) */
+int amgb_hierarchy_get_matrix(const amgb_hierarchy* h, int level, int* colptr, int* rowidx,
+                              double* val);
+int amgb_hierarchy_get_soln(amgb_hierarchy* h, int level, double* u);
+int amgb_hierarchy_get_rhs(amgb_hierarchy* h, int level, double* f);
+int amgb_hierarchy_set_soln(amgb_hierarchy* h, int level, const double* u);
+int amgb_hierarchy_set_rhs(amgb_hierarchy* h, int level, const double* f);
+/* colouring per level (COLOR_GS only) */
+int amgb_hierarchy_get_coloring(const amgb_hierarchy* h, int level, int* n_colors, int* color);
+
+/* one V-cycle on device-resident state (multigrid.hpp:263-305); asynchronous
+ * on the handle's stream */
+int amgb_vcycle(amgb_hierarchy* h);
+/* n back-to-back V-cycles, then a stream synchronise */
+int amgb_vcycles(amgb_hierarchy* h, int64_t n);
+/* sum r^2 on the finest level (common.hpp:17-27); synchronises */
+int amgb_hierarchy_rss(amgb_hierarchy* h, double* out);
+/* Multigrid::solve (multigrid.hpp:311-337).  Beyond the reference (which only
+ * prints them) the iteration count, last error and the error history are kept. */
+int amgb_solve(amgb_hierarchy* h, int64_t* iters_done, double* last_error);
+/* variant with the north star's criterion: stop when ||r||_2 / ||b||_2 <= rel_tol,
+ * checked every compute_error_every_n_iters cycles, capped at n_iters */
+int amgb_solve_relative(amgb_hierarchy* h, double rel_tol, int64_t* iters_done,
+                        double* last_rel_residual);
+int64_t amgb_hierarchy_iters_done(const amgb_hierarchy* h);
+/* copies min(cap, n) history entries, returns n */
+int64_t amgb_hierarchy_error_history(const amgb_hierarchy* h, double* out, int64_t cap);
+int amgb_synchronize(amgb_hierarchy* h);
+
+/* per-operator entry points on one level, host vectors in/out (parity tests).
+ * restriction: include/amg/interpolator.hpp:64-68; prolongation + add:
+ * interpolator.hpp:52-56 with multigrid.hpp:294-296. */
+int amgb_restrict(amgb_hierarchy* h, int level, const double* r_fine, double* f_coarse);
+int amgb_prolong_add(amgb_hierarchy* h, int level, const double* e_coarse, double* u_fine);
+/* smoother->smooth(A_l, u_l, f_l) on the device-resident level state */
+int amgb_smooth_level(amgb_hierarchy* h, int level);
+/* r_l = f_l - A_l u_l of the device-resident level state, copied to host */
+int amgb_residual_level(amgb_hierarchy* h, int level, double* r);
+/* fused residual + restriction as used inside the V-cycle: f_{l+1} = R_l (f_l - A_l u_l),
+ * u_{l+1} = 0 (multigrid.hpp:272-282) */
+int amgb_residual_restrict_level(amgb_hierarchy* h, int level);
+/* coarsest direct solve u_L = A_L^{-1} f_L (multigrid.hpp:287-288) */
+int amgb_coarse_solve(amgb_hierarchy* h);
+
+/* counters: kernels launched by this library in this process, and per V-cycle */
+int64_t amgb_kernel_launches(void);
+int64_t amgb_hierarchy_launches_per_vcycle(const amgb_hierarchy* h);
+
+/* algorithmic byte counts: B_l = 12 nnz_l + 28 N_l + 4 with
+ * nnz_l the entries the kernels stream (explicit zeros pruned) */
+int64_t amgb_hierarchy_pass_bytes(const amgb_hierarchy* h, int level);
+int64_t amgb_hierarchy_vcycle_bytes(const amgb_hierarchy* h);
+
+/* ------------------------------------------------------------------------
+ * Per-kernel timing hooks for bench.py (CUDA events on the handle's stream).
+ * kind: 0 smoother pass (one Jacobi sweep / one colour-complete pass / one GS
+ * direction), 1 residual, 2 residual+restrict, 3 prolong+add.  Runs `reps`
+ * launches after `warmup`, returns the mean milliseconds per launch.
+ * ---------------------------------------------------------------------- */
+int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int reps,
+                     double* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMGB_H_ */

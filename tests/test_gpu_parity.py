@@ -1,0 +1,348 @@
+"""GPU parity tests: every kernel of the V-cycle path, called through the C ABI
+(libamgb.so via ctypes), against the CPU oracle on the same deterministic
+inputs.  Tolerance: the north star allows 1e-12 relative in fp64; kernels that
+keep the reference's summation order are additionally required to be
+bit-identical to the oracle.  Integer maps must be bit-exact."""
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+amg = importlib.import_module("algebraic-multigrid_b200")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12  # BASELINE.json north_star: "within 1e-12 relative in fp64"
+
+
+def rel(a, b):
+    d = np.linalg.norm(a - b)
+    n = max(np.linalg.norm(b), 1e-300)
+    return d / n
+
+
+def problem(n, eps=1.0):
+    A = amg.Grid.laplacian(n, eps)
+    b = amg.Grid.rhs(n)
+    return A, b, O.laplacian(n, eps)
+
+
+def vec(n, seed):
+    return np.random.default_rng(seed).standard_normal(n)
+
+
+# ----------------------------------------------------------------- operators
+@pytest.mark.parametrize("n,eps", [(2, 1.0), (35, 1.0), (64, 1.0), (33, 1e-3), (200, 1.0)])
+def test_residual_bit_exact(n, eps):
+    A, b, Ao = problem(n, eps)
+    u = vec(n * n, 1)
+    r = amg.DeviceMatrix(A).residual(u, b)
+    assert r.tobytes() == O.residual(Ao, u, b).tobytes()
+
+
+@pytest.mark.parametrize("n", [2, 35, 200])
+def test_rss(n):
+    A, b, Ao = problem(n)
+    u = vec(n * n, 2) * 1e-3
+    got = amg.rss(A, u, b)
+    want = O.rss(Ao, u, b)
+    assert abs(got - want) <= 1e-13 * want
+
+
+@pytest.mark.parametrize("n,eps,sweeps", [(35, 1.0, 1), (35, 1.0, 2), (64, 1e-3, 3), (200, 1.0, 2)])
+def test_jacobi_bit_exact(n, eps, sweeps):
+    A, b, Ao = problem(n, eps)
+    AT = Ao.transpose()
+    u = vec(n * n, 3)
+    want = u.copy()
+    for _ in range(sweeps):
+        want = O.jacobi_sweep(AT, want, b, 0.6)
+    got = u.copy()
+    amg.DampedJacobi(0.6, sweeps).smooth(A, got, b)
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("n,eps", [(35, 1.0), (64, 1.0), (33, 1e-3)])
+def test_multicolor_gs_bit_exact(n, eps):
+    A, b, Ao = problem(n, eps)
+    AT = Ao.transpose()
+    nc_o, color_o = O.greedy_coloring(Ao, AT)
+    nc, color = amg.DeviceMatrix(A).coloring()
+    assert nc == nc_o == 2
+    np.testing.assert_array_equal(color, color_o)            # integer map: bit-exact
+    u = vec(n * n, 4)
+    want = u.copy()
+    for _ in range(2):
+        for c in list(range(nc_o)) + list(range(nc_o - 1, -1, -1)):
+            O.color_gs_pass(AT, color_o, c, b, want)
+    got = u.copy()
+    amg.MulticolorGaussSeidel(2).smooth(A, got, b)
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("n,eps", [(2, 1.0), (35, 1.0), (64, 1.0), (33, 1e-3)])
+def test_gauss_seidel_bit_exact(n, eps):
+    """Lexicographic forward+backward sweep == reference order (smoother.hpp:148-174)."""
+    A, b, Ao = problem(n, eps)
+    u = vec(n * n, 5)
+    want = u.copy()
+    O.gs_smooth(Ao, want, b, 1e-9, 0, 3)
+    got = u.copy()
+    sm = amg.SparseGaussSeidel()
+    sm.n_iters = 3
+    sm.smooth(A, got, b)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_spgs_as_solver_golden(capsys):
+    """testlib.cpp:188-196: SparseGaussSeidel(1e-9,100,1000) on the 35x35 system."""
+    A, b, Ao = problem(35)
+    u = np.zeros(1225)
+    sm = amg.SparseGaussSeidel(1e-9, 100, 1000)
+    sm.smooth(A, u, b)
+    assert sm.iters_done == 900
+    assert "SPGS converged after 900 iterations." in capsys.readouterr().out
+    err = amg.rss(A, u, b)
+    assert err < sm.tolerance
+    assert "%.6g" % err == "8.69692e-10"
+    uo = np.zeros(1225)
+    O.gs_smooth(Ao, uo, b, 1e-9, 100, 1000)
+    assert u.tobytes() == uo.tobytes()
+
+
+def test_four_dof_smoothers_reach_direct_solution():
+    """testlib.cpp:17-107 on the 2x2 grid."""
+    A, b, Ao = problem(2)
+    assert b.size == 4
+    exact = O.Ldlt(Ao).solve(b)
+    for sm in (amg.SparseGaussSeidel(100), amg.MulticolorGaussSeidel(100), amg.DampedJacobi(1.0, 100)):
+        u = np.zeros(4)
+        sm.smooth(A, u, b)
+        d = u - exact
+        assert np.dot(d, d) <= 1e-18 * min(np.dot(u, u), np.dot(exact, exact))   # isApprox(.,1e-9)
+
+
+# ----------------------------------------------------------------- hierarchy
+def make_pair(n, n_levels, smoother, eps=1.0, every=5, n_iters=100, **kw):
+    A, b, Ao = problem(n, eps)
+    kind = {amg.SMOOTHER_GS: O.SMOOTHER_GS, amg.SMOOTHER_JACOBI: O.SMOOTHER_JACOBI,
+            amg.SMOOTHER_COLOR_GS: O.SMOOTHER_COLOR_GS}[smoother.kind]
+    mo = O.Multigrid(Ao, b, n_levels, 1e-9, every, n_iters, kind, smoother.n_iters,
+                     getattr(smoother, "omega", 2.0 / 3.0))
+    li = amg.LinearInterpolator(n_levels)
+    mg = amg.Multigrid(li, smoother, A, b, n_levels, 1e-9, every, n_iters, **kw)
+    return mg, mo, li
+
+
+@pytest.mark.parametrize("n,L,eps", [(35, 8, 1.0), (64, 6, 1.0), (65, 9, 1e-3)])
+def test_hierarchy_maps_and_operators_bit_exact(n, L, eps):
+    mg, mo, li = make_pair(n, L, amg.SparseGaussSeidel(), eps)
+    for l in range(L):
+        assert mg.get_n_dofs(l) == mo.n_dofs(l)
+        M = mg.get_coefficient_matrix(l)
+        c, r, v = mo.A(l).arrays()
+        np.testing.assert_array_equal(M.colptr, c)       # structural pattern incl. explicit zeros
+        np.testing.assert_array_equal(M.rowidx, r)
+        assert M.val.tobytes() == v.tobytes()
+        assert mg.nnz(l) == mo.A(l).nnz
+        assert mg.nnz_device(l) == mo.A(l).nnz_nonzero
+    for l in range(L - 1):
+        c, r, v = mo.P(l).arrays()
+        np.testing.assert_array_equal(li.get_P(l).colptr, c)
+        np.testing.assert_array_equal(li.get_P(l).rowidx, r)
+        c, r, v = mo.R(l).arrays()
+        np.testing.assert_array_equal(li.get_R(l).colptr, c)
+        np.testing.assert_array_equal(li.get_R(l).rowidx, r)
+
+
+def test_level_shapes_decrease():
+    """testlib.cpp:167-181."""
+    mg, _, _ = make_pair(35, 8, amg.SparseGaussSeidel())
+    sizes = [mg.get_n_dofs(l) for l in range(8)]
+    assert sizes == [1225, 612, 305, 152, 75, 37, 18, 8]
+    for l in range(1, 8):
+        assert mg.get_soln(l - 1).size > mg.get_soln(l).size
+        assert mg.get_rhs(l - 1).size > mg.get_rhs(l).size
+
+
+@pytest.mark.parametrize("nh", [7, 24, 1225, 612, 305])
+def test_transfers_bit_exact(nh):
+    """restriction / prolongation+add incl. the even-n_h case whose last fine row is
+    in no column of P."""
+    nH = O.n_H_from_n_h(nh)
+    # a 2-level hierarchy whose fine level has nh rows: use a 1-D Laplacian-like CSC
+    colptr = np.arange(nh + 1, dtype=np.int32)
+    A = amg.CscMatrix(nh, nh, colptr, np.arange(nh, dtype=np.int32), -np.ones(nh))
+    mg = amg.Multigrid(None, amg.DampedJacobi(), A, np.ones(nh), 2, 1e-9, 1, 1)
+    P = O.make_P(nh, nH)
+    R = P.transpose()
+    r = vec(nh, 6)
+    assert mg.restrict(0, r).tobytes() == O.spmv(R, r).tobytes()
+    e, u = vec(nH, 7), vec(nh, 8)
+    assert mg.prolong_add(0, e, u).tobytes() == (u + O.spmv(P, e)).tobytes()
+
+
+@pytest.mark.parametrize("n,L,eps", [(35, 8, 1.0), (64, 5, 1.0), (33, 6, 1e-3)])
+def test_fused_residual_restrict_and_coarse_solve(n, L, eps):
+    mg, mo, _ = make_pair(n, L, amg.SparseGaussSeidel(), eps)
+    u0 = vec(n * n, 9)
+    mg.set_soln(0, u0)
+    mo.u(0)[:] = u0
+    # fused kernel == residual then restriction, and zeroes the coarse solution
+    mg.set_soln(1, np.ones(mg.get_n_dofs(1)))
+    mg.residual_restrict_level(0)
+    r = O.residual(mo.A(0), mo.u(0), mo.f(0))
+    assert mg.residual_level(0).tobytes() == r.tobytes()
+    assert mg.get_rhs(1).tobytes() == O.spmv(mo.R(0), r).tobytes()
+    assert not mg.get_soln(1).any()
+    # coarsest direct solve
+    fL = vec(mg.get_n_dofs(L - 1), 10)
+    mg.set_rhs(L - 1, fL)
+    mg.coarse_solve()
+    want = O.Ldlt(mo.A(L - 1)).solve(fL)
+    assert rel(mg.get_soln(L - 1), want) <= 1e-13
+    dense = mo.A(L - 1).to_scipy().toarray()
+    assert rel(dense @ mg.get_soln(L - 1), fL) <= 1e-10
+
+
+SMOOTHERS = [
+    ("gs", lambda: amg.SparseGaussSeidel()),
+    ("jacobi", lambda: amg.DampedJacobi(2.0 / 3.0, 2)),
+    ("color", lambda: amg.MulticolorGaussSeidel(1)),
+]
+
+
+@pytest.mark.parametrize("name,mk", SMOOTHERS)
+@pytest.mark.parametrize("n,L,eps", [(35, 8, 1.0), (64, 6, 1.0), (65, 9, 1e-3)])
+def test_vcycle_per_level_iterates(name, mk, n, L, eps):
+    """Per-level smoothed iterates after 1..3 V-cycles agree with the oracle."""
+    mg, mo, _ = make_pair(n, L, mk(), eps)
+    for cycle in range(3):
+        mg.vcycle()
+        mo.vcycle()
+        for l in range(L):
+            got, want = mg.get_soln(l), mo.u(l)
+            assert rel(got, want) <= RTOL, (name, cycle, l, rel(got, want))
+            if l + 1 < L or True:
+                assert rel(mg.get_rhs(l), mo.f(l)) <= RTOL or not mo.f(l).any()
+    # these kernels keep the oracle's operation order: expect identical bits on the fine level
+    assert mg.get_soln(0).tobytes() == mo.u(0).tobytes()
+
+
+def test_multicolor_maps_per_level_bit_exact():
+    mg, mo, _ = make_pair(35, 8, amg.MulticolorGaussSeidel(1))
+    for l in range(7):
+        nc, color = mg.coloring(l)
+        assert nc == mo.n_colors(l)
+        np.testing.assert_array_equal(color, mo.color(l))
+
+
+def test_amg_solve_golden(capsys):
+    """testlib.cpp:147-212 on the GPU: 35 cycles, error 7.19199e-11, AMG ~= SPGS."""
+    mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel())
+    A, b, _ = problem(35)
+    amg_u = mg.solve()
+    assert mg.iters_done == 35
+    assert "AMG converged after 35 iterations." in capsys.readouterr().out
+    mo.solve()
+    assert mo.iters_done == 35                                   # identical iteration counts
+    hist, hist_o = mg.error_history(), mo.history()
+    assert len(hist) == len(hist_o) == 7
+    np.testing.assert_allclose(hist, hist_o, rtol=RTOL)          # residual norms
+    amg_error = amg.rss(A, amg_u, b)
+    assert amg_error < mg.get_tolerance()                        # testlib.cpp:206
+    assert "%.6g" % amg_error == "7.19199e-11"                   # README screenshot
+    assert rel(amg_u, mo.u(0)) <= RTOL
+    spgs_u = np.zeros(1225)
+    amg.SparseGaussSeidel(1e-9, 100, 1000).smooth(A, spgs_u, b)
+    d = amg_u - spgs_u
+    assert np.dot(d, d) <= 1e-12 * min(np.dot(amg_u, amg_u), np.dot(spgs_u, spgs_u))  # :212
+
+
+@pytest.mark.parametrize("name,mk", SMOOTHERS[1:])
+def test_solve_iteration_counts_match_oracle(name, mk):
+    mg, mo, _ = make_pair(35, 8, mk(), every=5, n_iters=400)
+    mg.solve()
+    mo.solve()
+    assert mg.iters_done == mo.iters_done
+    np.testing.assert_allclose(mg.error_history(), mo.history(), rtol=RTOL)
+    assert mg.last_error <= 1e-9
+
+
+def test_solve_resumes_from_stored_solution():
+    """solve() continues from level_to_soln[0] (multigrid.hpp:101,336)."""
+    mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel(), every=5, n_iters=10)
+    mg.solve(); mo.solve()
+    assert mg.iters_done == mo.iters_done == 10
+    mg.solve(); mo.solve()
+    assert rel(mg.get_soln(0), mo.u(0)) <= RTOL
+    np.testing.assert_allclose(mg.error_history(), mo.history(), rtol=RTOL)
+
+
+def test_dead_coarse_smooth_is_unobservable_and_graph_equals_stream():
+    """The reference pre-smooths the coarsest level and then overwrites it with the direct
+    solve (multigrid.hpp:265-288); skipping that must not change any observable value.
+    A replayed CUDA graph must equal plain stream launches."""
+    base, _, _ = make_pair(35, 8, amg.SparseGaussSeidel())
+    full, _, _ = make_pair(35, 8, amg.SparseGaussSeidel(), skip_dead_coarse_smooth=False)
+    nograph, _, _ = make_pair(35, 8, amg.SparseGaussSeidel(), use_graph=False)
+    for m in (base, full, nograph):
+        m.vcycles(3)
+    for l in range(8):
+        assert base.get_soln(l).tobytes() == full.get_soln(l).tobytes()
+        assert base.get_soln(l).tobytes() == nograph.get_soln(l).tobytes()
+    assert base.launches_per_vcycle() > 0
+
+
+def test_relative_residual_criterion():
+    mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel(), every=1, n_iters=200)
+    A, b, Ao = problem(35)
+    mg.solve_relative(1e-8)
+    k = mg.iters_done
+    bn = np.linalg.norm(b)
+    for _ in range(k - 1):
+        mo.vcycle()
+    assert np.sqrt(mo.rss()) / bn > 1e-8
+    mo.vcycle()
+    assert np.sqrt(mo.rss()) / bn <= 1e-8
+    assert abs(mg.last_error - np.sqrt(mo.rss()) / bn) <= 1e-10 * mg.last_error
+
+
+# ----------------------------------------------------------------- larger sizes
+def test_jacobi_vcycle_1025():
+    """One full-size V-cycle (1025^2, 14 levels) against the oracle."""
+    n, L = 1025, 14
+    mg, mo, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), every=1, n_iters=1)
+    mg.vcycle()
+    mo.vcycle()
+    assert [mg.get_n_dofs(l) for l in range(L)] == O.level_sizes(n * n, L)
+    for l in range(L):
+        assert rel(mg.get_soln(l), mo.u(l)) <= RTOL
+    assert abs(mg.rss() - mo.rss()) <= 1e-12 * mo.rss()
+
+
+def test_properties_at_scale_4097():
+    """Size-independent properties at the BASELINE size (no oracle run needed):
+    linearity of the residual/restriction, R = P^T adjointness, Jacobi fixed point."""
+    n, L = 4097, 3
+    A = amg.Grid.laplacian(n)
+    b = amg.Grid.rhs(n)
+    mg = amg.Multigrid(None, amg.DampedJacobi(2.0 / 3.0, 2), A, b, L, 1e-9, 1, 1)
+    N0, N1 = mg.get_n_dofs(0), mg.get_n_dofs(1)
+    assert (N0, N1, mg.get_n_dofs(2)) == (16785409, 8392704, 4196351)
+    assert mg.nnz_device(0) == 5 * n * n - 4 * n
+    x, y = vec(N0, 11), vec(N0, 12)
+    # adjointness <R x, e> == <x, P e>
+    e = vec(N1, 13)
+    Rx = mg.restrict(0, x)
+    Pe = mg.prolong_add(0, e, np.zeros(N0))
+    assert abs(np.dot(Rx, e) - np.dot(x, Pe)) <= 1e-12 * np.linalg.norm(Rx) * np.linalg.norm(e)
+    # residual linearity: r(u1) - r(u2) == -A (u1 - u2) == r_{f=0}(u1 - u2)
+    mg.set_soln(0, x); r1 = mg.residual_level(0)
+    mg.set_soln(0, y); r2 = mg.residual_level(0)
+    mg.set_rhs(0, np.zeros(N0)); mg.set_soln(0, x - y); r3 = mg.residual_level(0)
+    assert rel(r1 - r2, r3) <= 1e-12
+    # the 5-point stencil applied to a constant: interior rows sum to zero
+    mg.set_soln(0, np.ones(N0)); r = mg.residual_level(0).reshape(n, n)
+    assert np.abs(r[1:-1, 1:-1]).max() <= 1e-6 * abs(A.val[2])
