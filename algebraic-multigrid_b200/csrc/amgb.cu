@@ -627,7 +627,18 @@ int amgb_hierarchy_create(int n_rows, int n_cols, const int* colptr, const int* 
     }
     h->partial.alloc(std::max(1, blocks_for(h->n[0], 256)));
     h->scalar.alloc(1);
-    // coarsest factorisation (multigrid.hpp:240-243)
+    // coarsest factorisation (multigrid.hpp:240-243); the direct solve is a banded
+    // substitution in one block, so refuse hierarchies whose coarsest level is not small
+    {
+      const Csc& Ac = h->ops[h->L - 1]->M;
+      int64_t bw = 0;
+      for (int c = 0; c < Ac.cols; ++c)
+        for (int p = Ac.colptr[c]; p < Ac.colptr[c + 1]; ++p) bw = std::max<int64_t>(bw, Ac.rowidx[p] - c);
+      if ((double)Ac.cols * (double)bw * (double)bw > 2e10 || (int64_t)Ac.cols * std::max<int64_t>(bw, 1) > (1ll << 27))
+        throw std::invalid_argument("coarsest level too large for the direct solve (" +
+                                    std::to_string(Ac.cols) + " DOF, half-bandwidth " +
+                                    std::to_string(bw) + "): use more levels");
+    }
     h->factor = factor_banded_ldlt(h->ops[h->L - 1]->M);
     h->dL.upload(h->factor.L, s);
     h->dd.upload(h->factor.d, s);

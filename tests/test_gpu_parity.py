@@ -325,9 +325,12 @@ def test_jacobi_vcycle_1025():
 def test_properties_at_scale_4097():
     """Size-independent properties at the BASELINE size (no oracle run needed):
     linearity of the residual/restriction, R = P^T adjointness, Jacobi fixed point."""
-    n, L = 4097, 3
+    n, L = 4097, 16
     A = amg.Grid.laplacian(n)
     b = amg.Grid.rhs(n)
+    with pytest.raises(amg.InvalidArgument, match="coarsest level too large"):
+        amg.Multigrid(None, amg.DampedJacobi(2.0 / 3.0, 2), amg.Grid.laplacian(1025),
+                      amg.Grid.rhs(1025), 2, 1e-9, 1, 1)
     mg = amg.Multigrid(None, amg.DampedJacobi(2.0 / 3.0, 2), A, b, L, 1e-9, 1, 1)
     N0, N1 = mg.get_n_dofs(0), mg.get_n_dofs(1)
     assert (N0, N1, mg.get_n_dofs(2)) == (16785409, 8392704, 4196351)
