@@ -102,6 +102,8 @@ SIGNATURES = {
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
     "amgb_hierarchy_pass_bytes": (_l, [_p, _i]),
     "amgb_hierarchy_vcycle_bytes": (_l, [_p]),
+    "amgb_hierarchy_format": (_i, [_p, _i]),
+    "amgb_hierarchy_matrix_bytes": (_l, [_p, _i]),
     "amgb_time_kernel": (_i, [_p, _i, _i, _i, _i, C.POINTER(_d)]),
 }
 
@@ -489,6 +491,12 @@ class Multigrid:
 
     def nnz_device(self, level):
         return lib().amgb_hierarchy_nnz_device(self.h, level)
+
+    def format(self, level):
+        return {0: "sell", 1: "dia"}[lib().amgb_hierarchy_format(self.h, level)]
+
+    def matrix_bytes(self, level):
+        return lib().amgb_hierarchy_matrix_bytes(self.h, level)
 
     def pass_bytes(self, level):
         return lib().amgb_hierarchy_pass_bytes(self.h, level)

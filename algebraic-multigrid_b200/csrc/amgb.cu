@@ -21,6 +21,7 @@
 namespace {
 
 using namespace amgb;
+using amgb::dev::DiaView;
 using amgb::dev::SellView;
 
 thread_local std::string g_err;
@@ -125,6 +126,70 @@ struct DevSell {
   SellView view() const { return SellView{n_rows, n_slices, slice_ptr.p, col.p, val.p, rows.p}; }
 };
 
+struct DevDia {
+  int n_rows = 0, n_cols = 0, ld = 0, n_diag = 0;
+  int64_t nnz = 0;
+  int off[dev::kMaxDiagDev] = {0};
+  DevBuf<double> val;
+  DevBuf<int> rows;
+  void upload(const Dia& D, cudaStream_t s) {
+    n_rows = D.n_rows;
+    n_cols = D.n_cols;
+    ld = D.ld;
+    n_diag = D.n_diag;
+    nnz = D.nnz;
+    for (int d = 0; d < n_diag; ++d) off[d] = D.off[d];
+    val.upload(D.val, s);
+    if (!D.rows.empty()) rows.upload(D.rows, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  DiaView view() const {
+    DiaView v;
+    v.n_rows = n_rows;
+    v.n_cols = n_cols;
+    v.ld = ld;
+    v.n_diag = n_diag;
+    for (int d = 0; d < dev::kMaxDiagDev; ++d) v.off[d] = off[d];
+    v.val = val.p;
+    v.rows = rows.p;
+    return v;
+  }
+};
+
+// One device matrix: DIA when the operator is banded enough, else SELL-32.
+struct DevMat {
+  bool is_dia = false;
+  DevDia dia;
+  DevSell sell;
+  void upload(const Csc& M, const std::vector<int>* rows, cudaStream_t s, bool allow_dia = true) {
+    Dia D;
+    if (allow_dia) D = build_dia(M, rows);
+    is_dia = D.ok;
+    if (is_dia) dia.upload(D, s);
+    else sell.upload(build_sell(M, rows), s);
+  }
+  int n_rows() const { return is_dia ? dia.n_rows : sell.n_rows; }
+  int64_t nnz() const { return is_dia ? dia.nnz : sell.nnz; }
+  // bytes of matrix data one pass streams
+  int64_t stored_bytes() const {
+    return is_dia ? (int64_t)dia.val.n * 8 + (int64_t)dia.rows.n * 4
+                  : (int64_t)sell.val.n * 12 + (int64_t)sell.slice_ptr.n * 4 + (int64_t)sell.rows.n * 4;
+  }
+};
+template <int ND>
+dev::DiaViewT<ND> dia_view_t(const DevDia& d) {
+  dev::DiaViewT<ND> v;
+  static_cast<DiaView&>(v) = d.view();
+  return v;
+}
+template <class Fn>
+void with_view(const DevMat& m, Fn&& fn) {
+  if (!m.is_dia) fn(m.sell.view());
+  else if (m.dia.n_diag <= 6) fn(dia_view_t<6>(m.dia));
+  else if (m.dia.n_diag <= 10) fn(dia_view_t<10>(m.dia));
+  else fn(dia_view_t<16>(m.dia));
+}
+
 inline int blocks_for(int64_t n, int per_block) { return (int)((n + per_block - 1) / per_block); }
 
 // Device mirror of one operator plus the lazily built smoother schedules.
@@ -133,8 +198,8 @@ struct Operator {
   Csc MT;                 // transpose (rows of A); built once
   bool symmetric = true;  // M == MT bitwise
   int n = 0;
-  DevSell colrows;                  // SELL row c = CSC column c (smoother.hpp:101-117)
-  std::unique_ptr<DevSell> arows;   // SELL rows of A when !symmetric
+  DevMat colrows;                   // row c = CSC column c (smoother.hpp:101-117)
+  std::unique_ptr<DevMat> arows;    // rows of A when !symmetric
   // generic Gauss-Seidel fronts
   bool have_fronts = false;
   DevBuf<int> f_order, f_ptr, b_order, b_ptr;
@@ -143,7 +208,7 @@ struct Operator {
   bool have_colors = false;
   int n_colors = 0;
   std::vector<int> color;
-  std::vector<std::unique_ptr<DevSell>> color_sell;
+  std::vector<std::unique_ptr<DevMat>> color_sell;
 
   void build(Csc&& A, cudaStream_t s) {
     if (A.rows != A.cols) throw std::invalid_argument("operator must be square");
@@ -151,13 +216,13 @@ struct Operator {
     n = M.cols;
     MT = transpose(M);
     symmetric = bitwise_equal(M, MT);
-    colrows.upload(build_sell(M), s);
+    colrows.upload(M, nullptr, s);
     if (!symmetric) {
-      arows.reset(new DevSell());
-      arows->upload(build_sell(MT), s);
+      arows.reset(new DevMat());
+      arows->upload(MT, nullptr, s);
     }
   }
-  const DevSell& rows_of_A() const { return symmetric ? colrows : *arows; }
+  const DevMat& rows_of_A() const { return symmetric ? colrows : *arows; }
   const Csc& host_rows_of_A() const { return symmetric ? M : MT; }  // CSC whose column k = row k of A
 
   void ensure_fronts(cudaStream_t s) {
@@ -179,37 +244,67 @@ struct Operator {
     for (int k = 0; k < n; ++k) members[color[k]].push_back(k);
     color_sell.clear();
     for (int c = 0; c < n_colors; ++c) {
-      color_sell.emplace_back(new DevSell());
-      color_sell.back()->upload(build_sell(host_rows_of_A(), &members[c]), s);
+      color_sell.emplace_back(new DevMat());
+      color_sell.back()->upload(host_rows_of_A(), &members[c], s);
     }
     have_colors = true;
   }
 
   // ---- launches (all asynchronous on s) ----
   void residual(const double* u, const double* f, double* r, cudaStream_t s) const {
-    if (n) LAUNCH(dev::k_residual, blocks_for(n, 256), 256, 0, s, rows_of_A().view(), u, f, r);
+    if (!n) return;
+    with_view(rows_of_A(), [&](auto V) {
+      auto kern = dev::k_residual<decltype(V)>;
+      LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, r);
+    });
   }
   void jacobi(const double* u, const double* f, double omega, double* out, cudaStream_t s) const {
-    if (n) LAUNCH(dev::k_jacobi, blocks_for(n, 256), 256, 0, s, rows_of_A().view(), u, f, omega, out);
+    if (!n) return;
+    with_view(rows_of_A(), [&](auto V) {
+      auto kern = dev::k_jacobi<decltype(V)>;
+      LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, omega, out);
+    });
   }
   void color_pass(int c, const double* f, double* u, cudaStream_t s) const {
-    const DevSell& C = *color_sell[c];
-    if (C.n_rows) LAUNCH(dev::k_color_gs, blocks_for(C.n_rows, 256), 256, 0, s, C.view(), f, u);
+    const DevMat& C = *color_sell[c];
+    if (!C.n_rows()) return;
+    with_view(C, [&](auto V) {
+      auto kern = dev::k_color_gs<decltype(V)>;
+      LAUNCH(kern, blocks_for(V.n_rows, 256), 256, 0, s, V, f, u);
+    });
+  }
+  void gs_fronts(const int* order, const int* ptr, int n_fronts, const double* f, double* u,
+                 cudaStream_t s) const {
+    if (!n) return;
+    with_view(colrows, [&](auto V) {
+      auto kern = dev::k_gs_fronts<decltype(V)>;
+      LAUNCH(kern, 1, 1024, 0, s, V, order, ptr, n_fronts, f, u);
+    });
   }
   void gs_forward(const double* f, double* u, cudaStream_t s) const {
-    if (n) LAUNCH(dev::k_gs_fronts, 1, 1024, 0, s, colrows.view(), f_order.p, f_ptr.p, n_ffronts, f, u);
+    gs_fronts(f_order.p, f_ptr.p, n_ffronts, f, u, s);
   }
   void gs_backward(const double* f, double* u, cudaStream_t s) const {
-    if (n) LAUNCH(dev::k_gs_fronts, 1, 1024, 0, s, colrows.view(), b_order.p, b_ptr.p, n_bfronts, f, u);
+    gs_fronts(b_order.p, b_ptr.p, n_bfronts, f, u, s);
+  }
+  void residual_restrict(const double* u, const double* f, double* f_coarse, double* u_coarse,
+                         int n_coarse, cudaStream_t s) const {
+    with_view(rows_of_A(), [&](auto V) {
+      auto kern = dev::k_residual_restrict<decltype(V)>;
+      LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, f_coarse, u_coarse, n_coarse);
+    });
   }
   int rss_blocks() const { return std::max(1, blocks_for(n, 256)); }
   // partial must hold rss_blocks() doubles; out one double
   void rss(const double* u, const double* b, double* partial, double* out, cudaStream_t s) const {
     const int nb = rss_blocks();
-    LAUNCH(dev::k_rss_partial, nb, 256, 0, s, rows_of_A().view(), u, b, partial);
+    with_view(rows_of_A(), [&](auto V) {
+      auto kern = dev::k_rss_partial<decltype(V)>;
+      LAUNCH(kern, nb, 256, 0, s, V, u, b, partial);
+    });
     LAUNCH(dev::k_sum_partials, 1, 256, 0, s, partial, nb, out);
   }
-  int64_t nnz_device() const { return rows_of_A().nnz; }
+  int64_t nnz_device() const { return rows_of_A().nnz(); }
 };
 
 void options_default(amgb_options* o) {
@@ -258,6 +353,7 @@ struct amgb_hierarchy {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int64_t launches_per_vcycle = 0;
+  bool ldlt_attr_set = false;
   int64_t iters_done = 0;
   std::vector<double> history;
 
@@ -299,8 +395,7 @@ struct amgb_hierarchy {
   }
   // f_{l+1} = R_l (f_l - A_l u_l), u_{l+1} = 0   (multigrid.hpp:272-282)
   void residual_restrict(int l, cudaStream_t s) {
-    LAUNCH(dev::k_residual_restrict, blocks_for(n[l], 256), 256, 0, s, ops[l]->rows_of_A().view(),
-           u[l].p, f[l].p, f[l + 1].p, u[l + 1].p, (int)n[l + 1]);
+    ops[l]->residual_restrict(u[l].p, f[l].p, f[l + 1].p, u[l + 1].p, (int)n[l + 1], s);
   }
   // u_l = u_l + P_l u_{l+1}   (multigrid.hpp:294-296)
   void prolong_add(int l, cudaStream_t s) {
@@ -310,10 +405,19 @@ struct amgb_hierarchy {
   void coarse_solve(cudaStream_t s) {  // multigrid.hpp:287-288
     const int nc = factor.n, bw = factor.bw;
     int threads = std::min(1024, std::max(32, ((bw + 31) / 32) * 32));
-    const size_t bytes = sizeof(double) * (size_t)nc;
-    const int use_smem = bytes <= 48 * 1024;
-    LAUNCH(dev::k_banded_ldlt_solve, 1, threads, use_smem ? bytes : 0, s, dL.p, dd.p, nc, bw,
-           f[L - 1].p, u[L - 1].p, dwork.p, use_smem);
+    const size_t xbytes = sizeof(double) * (size_t)nc;
+    const size_t lbytes = sizeof(double) * (size_t)nc * std::max(bw, 1);
+    const size_t cap = 200 * 1024;
+    const int x_smem = xbytes <= cap;
+    const int l_smem = x_smem && xbytes + lbytes <= cap;
+    const size_t smem = (x_smem ? xbytes : 0) + (l_smem ? lbytes : 0);
+    if (smem > 48 * 1024 && !ldlt_attr_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(dev::k_banded_ldlt_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)cap));
+      ldlt_attr_set = true;
+    }
+    LAUNCH(dev::k_banded_ldlt_solve, 1, threads, smem, s, dL.p, dd.p, nc, bw, f[L - 1].p, u[L - 1].p,
+           dwork.p, x_smem, l_smem);
   }
   void enqueue_vcycle(cudaStream_t s) {
     for (int l = 0; l < L; ++l) {
@@ -892,6 +996,15 @@ int64_t amgb_hierarchy_vcycle_bytes(const amgb_hierarchy* h) {
   return total;
 }
 
+int amgb_hierarchy_format(const amgb_hierarchy* h, int level) {
+  if (!h || level < 0 || level >= h->L) return -1;
+  return h->ops[level]->rows_of_A().is_dia ? AMGB_FORMAT_DIA : AMGB_FORMAT_SELL;
+}
+int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level) {
+  if (!h || level < 0 || level >= h->L) return -1;
+  return h->ops[level]->rows_of_A().stored_bytes();
+}
+
 int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int reps, double* ms_out) {
   return guarded([&] {
     if (!h || !ms_out || reps < 1) throw std::invalid_argument("bad argument");
@@ -924,8 +1037,7 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
           A.residual(scratch_u.p, h->f[level].p, h->tmp[level].p, s);
           break;
         case 2:
-          LAUNCH(dev::k_residual_restrict, blocks_for(h->n[level], 256), 256, 0, s, A.rows_of_A().view(),
-                 scratch_u.p, h->f[level].p, scratch_c2.p, scratch_c.p, (int)h->n[level + 1]);
+          A.residual_restrict(scratch_u.p, h->f[level].p, scratch_c2.p, scratch_c.p, (int)h->n[level + 1], s);
           break;
         case 3:
           LAUNCH(dev::k_prolong_add, blocks_for(h->n[level], 256), 256, 0, s, scratch_c.p,

@@ -288,6 +288,51 @@ Sell build_sell(const Csc& M, const std::vector<int>* rows) {
   return S;
 }
 
+// ------------------------------------------------------------------ DIA
+
+Dia build_dia(const Csc& M, const std::vector<int>* rows) {
+  Dia D;
+  const int n = rows ? static_cast<int>(rows->size()) : M.cols;
+  auto row_of = [&](int t) { return rows ? (*rows)[t] : t; };
+  // distinct offsets col - row over the non-zero entries of the covered rows
+  std::vector<int> offs;
+  int64_t nnz = 0;
+  for (int t = 0; t < n; ++t) {
+    const int r = row_of(t);
+    for (int p = M.colptr[r]; p < M.colptr[r + 1]; ++p) {
+      if (M.val[p] == 0.0) continue;
+      ++nnz;
+      const int o = M.rowidx[p] - r;
+      auto it = std::lower_bound(offs.begin(), offs.end(), o);
+      if (it == offs.end() || *it != o) {
+        if (static_cast<int>(offs.size()) == kMaxDiag) return D;  // not banded enough
+        offs.insert(it, o);
+      }
+    }
+  }
+  const int ld = (n + 31) / 32 * 32;
+  // refuse when diagonal storage would stream >25% more bytes than SELL (12 B / entry)
+  if (8.0 * offs.size() * ld > 1.25 * 12.0 * static_cast<double>(nnz) + 4096.0) return D;
+  D.ok = true;
+  D.n_rows = n;
+  D.n_cols = M.rows;
+  D.ld = ld;
+  D.n_diag = static_cast<int>(offs.size());
+  D.nnz = nnz;
+  D.off = offs;
+  D.val.assign(static_cast<size_t>(D.n_diag) * ld, 0.0);
+  if (rows) D.rows = *rows;
+  for (int t = 0; t < n; ++t) {
+    const int r = row_of(t);
+    for (int p = M.colptr[r]; p < M.colptr[r + 1]; ++p) {
+      if (M.val[p] == 0.0) continue;
+      const int d = static_cast<int>(std::lower_bound(offs.begin(), offs.end(), M.rowidx[p] - r) - offs.begin());
+      D.val[static_cast<size_t>(d) * ld + t] = M.val[p];
+    }
+  }
+  return D;
+}
+
 // ------------------------------------------------------------------ GS schedule
 
 Schedule gs_schedule(const Csc& M, bool forward) {

@@ -69,6 +69,27 @@ struct Sell {
 };
 Sell build_sell(const Csc& M, const std::vector<int>* rows = nullptr);
 
+// ---- DIA layout (diagonal storage) of "row c = CSC column c" ----
+// For the banded operators of this path (5/7/9 distinct offsets per level) the
+// column index of entry d of row r is r + off[d], so no index array is
+// streamed and the x gathers do not depend on a prior load.  val[d*ld + t] is
+// the entry of the t-th covered row on diagonal d (0.0 = absent; explicit
+// zeros are dropped exactly like in the SELL layout).  off is ascending, so
+// walking d = 0.. keeps the reference's ascending-column summation order.
+struct Dia {
+  bool ok = false;   // false: too many distinct offsets, use SELL
+  int n_rows = 0;
+  int n_cols = 0;
+  int ld = 0;        // n_rows rounded up to 32
+  int n_diag = 0;
+  int64_t nnz = 0;   // real entries
+  std::vector<int> off;
+  std::vector<double> val;  // n_diag * ld
+  std::vector<int> rows;    // optional row subset
+};
+constexpr int kMaxDiag = 16;
+Dia build_dia(const Csc& M, const std::vector<int>* rows = nullptr);
+
 // ---- Gauss-Seidel wavefront schedule on the pruned dependency DAG ----
 // forward: row k depends on rows j<k with M(j,k) != 0 (column k of M used as
 // row k); backward: rows j>k.  order lists rows grouped by wavefront.

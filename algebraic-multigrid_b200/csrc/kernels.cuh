@@ -1,8 +1,11 @@
 // Device kernels of the V-cycle path (sm_100a).  All of them are HBM-bound
-// streaming kernels over the SELL-32 mirror (host_setup.hpp): one thread per
-// matrix row, a warp per 32-row slice, so every load of col/val is a full
-// 128/256-byte coalesced request and, for the banded operators of this path,
-// so are the gathers of x.  Each thread walks its row in ascending column
+// streaming kernels over a device mirror in one of two layouts (host_setup.hpp):
+//   DIA      diagonal storage for banded operators (all levels of this path):
+//            no index array, x gathers independent of any prior load;
+//   SELL-32  sliced ELL with explicit column indices for everything else.
+// One thread per matrix row, a warp per 32 consecutive rows, so every load of
+// val (and col) is a full 256/128-byte coalesced request and, for banded
+// operators, so are the gathers of x.  Each thread walks its row in ascending column
 // order with explicit __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn (never contracted
 // into FMAs), which reproduces the reference's summation order bit for bit:
 //   Gauss-Seidel update   include/amg/smoother.hpp:101-138
@@ -26,10 +29,43 @@ struct SellView {
   const int* rows;            // row ids when the view is a subset, else nullptr
 };
 
+constexpr int kMaxDiagDev = 16;
+struct DiaView {
+  int n_rows;   // rows covered by this view
+  int n_cols;   // length of x
+  int ld;       // leading dimension of val (n_rows rounded up to 32)
+  int n_diag;
+  int off[kMaxDiagDev];  // ascending column offsets
+  const double* val;     // val[d*ld + t], 0.0 = no entry
+  const int* rows;       // row ids when the view is a subset, else nullptr
+};
+
+// Compile-time bound on the number of diagonals, so the walk below is fully
+// unrolled and off[] is read straight from the constant bank.
+template <int ND>
+struct DiaViewT : DiaView {};
+
+// Visit the entries of DIA row t (matrix row `row`) in ascending column order.
+// All val loads and all x gathers are independent of each other (x index =
+// row + off, clamped; an absent entry has val == 0 and is skipped).
+template <int ND, class Fn>
+__device__ __forceinline__ void for_each_entry(const DiaViewT<ND>& S, int t, int row, const double* x, Fn&& fn) {
+  const double* vp = S.val + t;
+  const int last = S.n_cols - 1;
+  double v[ND], xv[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) v[d] = (d < S.n_diag) ? vp[(size_t)d * S.ld] : 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) xv[d] = (d < S.n_diag) ? x[min(max(row + S.off[d], 0), last)] : 0.0;
+#pragma unroll
+  for (int d = 0; d < ND; ++d)
+    if (v[d] != 0.0) fn(row + S.off[d], v[d], xv[d]);
+}
+
 // Visit the entries of SELL row t in ascending column order.  Loads are
 // batched four at a time (4 col + 4 val loads in flight, then 4 gathers).
 template <class Fn>
-__device__ __forceinline__ void for_each_entry(const SellView& S, int t, const double* x, Fn&& fn) {
+__device__ __forceinline__ void for_each_entry(const SellView& S, int t, int /*row*/, const double* x, Fn&& fn) {
   const int s = t >> 5;
   const uint32_t begin = S.slice_ptr[s] + (t & 31);
   const uint32_t end = S.slice_ptr[s + 1];
@@ -55,19 +91,21 @@ __device__ __forceinline__ void for_each_entry(const SellView& S, int t, const d
 }
 
 // ((f - a1 x1) - a2 x2) - ...   (multigrid.hpp:272-274)
-__device__ __forceinline__ double row_residual(const SellView& S, int t, const double* x, double f) {
+template <class M>
+__device__ __forceinline__ double row_residual(const M& S, int t, int row, const double* x, double f) {
   double acc = f;
-  for_each_entry(S, t, x, [&](int, double a, double xv) { acc = __dsub_rn(acc, __dmul_rn(a, xv)); });
+  for_each_entry(S, t, row, x, [&](int, double a, double xv) { acc = __dsub_rn(acc, __dmul_rn(a, xv)); });
   return acc;
 }
 
 // The reference's Gauss-Seidel row update (smoother.hpp:101-138): rsum from +0,
 // off-diagonal terms added in ascending order, (b - rsum) / diag, skipped when
 // the diagonal is zero or absent.
-__device__ __forceinline__ double row_gs(const SellView& S, int t, int row, const double* x, double b,
+template <class M>
+__device__ __forceinline__ double row_gs(const M& S, int t, int row, const double* x, double b,
                                          double keep) {
   double rsum = 0.0, diag = 0.0;
-  for_each_entry(S, t, x, [&](int c, double a, double xv) {
+  for_each_entry(S, t, row, x, [&](int c, double a, double xv) {
     if (c == row) diag = a;
     else rsum = __dadd_rn(rsum, __dmul_rn(a, xv));
   });
@@ -75,22 +113,24 @@ __device__ __forceinline__ double row_gs(const SellView& S, int t, int row, cons
 }
 
 // ------------------------------------------------------------------ residual
-__global__ void __launch_bounds__(256) k_residual(SellView A, const double* __restrict__ u,
+template <class M>
+__global__ void __launch_bounds__(256) k_residual(M A, const double* __restrict__ u,
                                                   const double* __restrict__ f, double* __restrict__ r) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= A.n_rows) return;
-  r[t] = row_residual(A, t, u, f[t]);
+  r[t] = row_residual(A, t, t, u, f[t]);
 }
 
 // ------------------------------------------------------------------ damped Jacobi
 // u_new[k] = u[k] + omega * (r_k / a_kk), r_k as in k_residual.
-__global__ void __launch_bounds__(256) k_jacobi(SellView A, const double* __restrict__ u,
+template <class M>
+__global__ void __launch_bounds__(256) k_jacobi(M A, const double* __restrict__ u,
                                                 const double* __restrict__ f, double omega,
                                                 double* __restrict__ u_new) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= A.n_rows) return;
   double acc = f[t], diag = 0.0;
-  for_each_entry(A, t, u, [&](int c, double a, double xv) {
+  for_each_entry(A, t, t, u, [&](int c, double a, double xv) {
     if (c == t) diag = a;
     acc = __dsub_rn(acc, __dmul_rn(a, xv));
   });
@@ -100,7 +140,8 @@ __global__ void __launch_bounds__(256) k_jacobi(SellView A, const double* __rest
 
 // ------------------------------------------------------------------ multicolour GS
 // One colour: the view lists the rows of that colour; they only read other colours.
-__global__ void __launch_bounds__(256) k_color_gs(SellView C, const double* __restrict__ f, double* u) {
+template <class M>
+__global__ void __launch_bounds__(256) k_color_gs(M C, const double* __restrict__ f, double* u) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= C.n_rows) return;
   const int row = C.rows[t];
@@ -112,23 +153,43 @@ __global__ void __launch_bounds__(256) k_color_gs(SellView C, const double* __re
 // wavefront of the (zero-pruned) dependency DAG are independent; fronts run in
 // order inside ONE block (block barrier between fronts).  This is the fallback
 // for operators the systolic kernel does not cover; it is latency-bound.
-__global__ void __launch_bounds__(1024) k_gs_fronts(SellView A, const int* __restrict__ order,
+// entry walkers that read u with ld.global.cg (L2): values written by other
+// threads of the block in an earlier front must be seen
+template <class Fn>
+__device__ __forceinline__ void for_each_entry_cg(const SellView& A, int row, const double* u, Fn&& fn) {
+  const int s = row >> 5;
+  const uint32_t begin = A.slice_ptr[s] + (row & 31), end = A.slice_ptr[s + 1];
+  for (uint32_t p = begin; p < end; p += 32) {
+    const int c = A.col[p];
+    if (c < 0) break;
+    fn(c, A.val[p], __ldcg(u + c));
+  }
+}
+template <int ND, class Fn>
+__device__ __forceinline__ void for_each_entry_cg(const DiaViewT<ND>& A, int row, const double* u, Fn&& fn) {
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    if (d >= A.n_diag) break;
+    const double a = A.val[(size_t)d * A.ld + row];
+    if (a != 0.0) {
+      const int c = row + A.off[d];
+      fn(c, a, __ldcg(u + c));
+    }
+  }
+}
+template <class M>
+__global__ void __launch_bounds__(1024) k_gs_fronts(M A, const int* __restrict__ order,
                                                     const int* __restrict__ front_ptr, int n_fronts,
                                                     const double* __restrict__ f, double* u) {
   for (int fr = 0; fr < n_fronts; ++fr) {
     const int b = front_ptr[fr], e = front_ptr[fr + 1];
     for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
       const int row = order[i];
-      const int s = row >> 5;
-      const uint32_t begin = A.slice_ptr[s] + (row & 31), end = A.slice_ptr[s + 1];
       double rsum = 0.0, diag = 0.0;
-      for (uint32_t p = begin; p < end; p += 32) {
-        const int c = A.col[p];
-        if (c < 0) break;
-        const double a = A.val[p];
+      for_each_entry_cg(A, row, u, [&](int c, double a, double xv) {
         if (c == row) diag = a;
-        else rsum = __dadd_rn(rsum, __dmul_rn(a, __ldcg(u + c)));
-      }
+        else rsum = __dadd_rn(rsum, __dmul_rn(a, xv));
+      });
       if (diag != 0.0) __stcg(u + row, __ddiv_rn(__dsub_rn(f[row], rsum), diag));
     }
     __syncthreads();
@@ -140,7 +201,8 @@ __global__ void __launch_bounds__(1024) k_gs_fronts(SellView A, const int* __res
 // written to HBM; also zeroes the coarse solution (multigrid.hpp:272-282).
 // A block owns 256 fine rows and the 128 coarse rows centred in them; the one
 // extra fine row 2J+2 of its last coarse row is recomputed by thread 0.
-__global__ void __launch_bounds__(256) k_residual_restrict(SellView A, const double* __restrict__ u,
+template <class M>
+__global__ void __launch_bounds__(256) k_residual_restrict(M A, const double* __restrict__ u,
                                                            const double* __restrict__ f,
                                                            double* __restrict__ f_coarse,
                                                            double* __restrict__ u_coarse, int n_coarse) {
@@ -148,10 +210,10 @@ __global__ void __launch_bounds__(256) k_residual_restrict(SellView A, const dou
   const int base = blockIdx.x * 256;
   const int t = threadIdx.x;
   const int row = base + t;
-  r[t] = (row < A.n_rows) ? row_residual(A, row, u, f[row]) : 0.0;
+  r[t] = (row < A.n_rows) ? row_residual(A, row, row, u, f[row]) : 0.0;
   if (t == 0) {
     const int extra = base + 256;
-    r[256] = (extra < A.n_rows) ? row_residual(A, extra, u, f[extra]) : 0.0;
+    r[256] = (extra < A.n_rows) ? row_residual(A, extra, extra, u, f[extra]) : 0.0;
   }
   __syncthreads();
   if (t < 128) {
@@ -218,7 +280,8 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
   }
   return tot;  // valid in thread 0
 }
-__global__ void __launch_bounds__(256) k_rss_partial(SellView A, const double* __restrict__ u,
+template <class M>
+__global__ void __launch_bounds__(256) k_rss_partial(M A, const double* __restrict__ u,
                                                      const double* __restrict__ b,
                                                      double* __restrict__ partial) {
   __shared__ double sh[32];
@@ -226,7 +289,7 @@ __global__ void __launch_bounds__(256) k_rss_partial(SellView A, const double* _
   double sq = 0.0;
   if (t < A.n_rows) {
     double bhat = 0.0;
-    for_each_entry(A, t, u, [&](int, double a, double xv) { bhat = __dadd_rn(bhat, __dmul_rn(a, xv)); });
+    for_each_entry(A, t, t, u, [&](int, double a, double xv) { bhat = __dadd_rn(bhat, __dmul_rn(a, xv)); });
     const double d = __dsub_rn(b[t], bhat);
     sq = __dmul_rn(d, d);
   }
@@ -260,17 +323,23 @@ __global__ void __launch_bounds__(1024) k_banded_ldlt_solve(const double* __rest
                                                             const double* __restrict__ d, int n, int bw,
                                                             const double* __restrict__ f,
                                                             double* __restrict__ x_out, double* work,
-                                                            int use_smem) {
-  extern __shared__ double sx[];
-  double* x = use_smem ? sx : work;
+                                                            int x_in_smem, int L_in_smem) {
+  extern __shared__ double sm[];
+  double* x = x_in_smem ? sm : work;
   const int ld = bw > 0 ? bw : 1;
+  const double* Lp = L;
+  if (L_in_smem) {
+    double* sL = sm + (x_in_smem ? n : 0);
+    for (size_t i = threadIdx.x; i < (size_t)n * ld; i += blockDim.x) sL[i] = L[i];
+    Lp = sL;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = f[i];
   __syncthreads();
   for (int i = 0; i < n; ++i) {
     const double xi = x[i];
     for (int t = 1 + threadIdx.x; t <= bw; t += blockDim.x) {
       const int r = i + t;
-      if (r < n) x[r] = __dsub_rn(x[r], __dmul_rn(L[(size_t)r * ld + (i - (r - bw))], xi));
+      if (r < n) x[r] = __dsub_rn(x[r], __dmul_rn(Lp[(size_t)r * ld + (i - (r - bw))], xi));
     }
     __syncthreads();
   }
@@ -280,7 +349,7 @@ __global__ void __launch_bounds__(1024) k_banded_ldlt_solve(const double* __rest
     const double xi = x[i];
     for (int t = 1 + threadIdx.x; t <= bw; t += blockDim.x) {
       const int c = i - t;
-      if (c >= 0) x[c] = __dsub_rn(x[c], __dmul_rn(L[(size_t)i * ld + (c - (i - bw))], xi));
+      if (c >= 0) x[c] = __dsub_rn(x[c], __dmul_rn(Lp[(size_t)i * ld + (c - (i - bw))], xi));
     }
     __syncthreads();
   }

@@ -201,6 +201,12 @@ int amgb_coarse_solve(amgb_hierarchy* h);
 int64_t amgb_kernel_launches(void);
 int64_t amgb_hierarchy_launches_per_vcycle(const amgb_hierarchy* h);
 
+/* device layout of a level's operator and the matrix bytes one pass really streams */
+#define AMGB_FORMAT_SELL 0 /* sliced ELL, 32 rows per slice, explicit column indices */
+#define AMGB_FORMAT_DIA 1  /* diagonal storage (banded operators): no index array     */
+int amgb_hierarchy_format(const amgb_hierarchy* h, int level);
+int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level);
+
 /* algorithmic byte counts: B_l = 12 nnz_l + 28 N_l + 4 with
  * nnz_l the entries the kernels stream (explicit zeros pruned) */
 int64_t amgb_hierarchy_pass_bytes(const amgb_hierarchy* h, int level);
