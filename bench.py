@@ -197,10 +197,10 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     # ---- device-resident V-cycles (value) ----
+    sampler = ClockSampler(local) if rank == 0 else None   # samples warm-up + timed region
     for _ in range(a.warmup):
         mg.vcycle()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = amg.kernel_launches()
     e0.record(stream)
@@ -244,22 +244,36 @@ def run_b200(a):
                "h2d_bytes_per_step": 16 * N0, "d2h_bytes_per_step": 8 * N0, "steps": steps_e}
 
     # ---- dominant kernel roofline: the level-0 smoother pass, timed live with CUDA events ----
+    # Algorithmic bytes of one pass over level l for the layout the kernel streams
+    # (DESIGN.md "bytes per unit"): stored matrix bytes (DIA: 8 B x diagonals x rows, no
+    # index array; SELL: 12 B per stored entry) + f read + u read + result write (24 N).
+    # The CSR-based figure of SURVEY.md 8(d) (12 nnz + 28 N + 4) is reported beside it.
     peak, peak_src = measured_hbm_peak()
     kern_ms = mg.time_kernel(0, 0, warmup=3, reps=20)
-    bytes0 = mg.pass_bytes(0)
+    n1 = mg.get_n_dofs(1)
+    bytes0 = mg.matrix_bytes(0) + 24 * N0
+    survey0 = mg.pass_bytes(0)
     achieved = bytes0 / (kern_ms * 1e-3) / 1e9
     kname = {"jacobi": "k_jacobi", "color": "k_color_gs", "gs": "k_gs_fronts"}[a.smoother]
-    roofline = {"bound": "hbm", "kernel": kname + " (level 0)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": kname + " (level 0, %s layout)" % mg.format(0),
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes0, "ms_per_launch": kern_ms,
+                "survey_formula_bytes_per_launch": survey0,
+                "survey_formula_GBps": survey0 / (kern_ms * 1e-3) / 1e9,
                 "traffic": ncu_traffic(kname)}
     per_kernel = {}
     for kind, nm in ((1, "residual"), (2, "residual_restrict"), (3, "prolong_add")):
         t_ms = mg.time_kernel(0, kind, warmup=3, reps=20)
-        n1 = mg.get_n_dofs(1)
-        alg = {1: bytes0, 2: 12 * mg.nnz_device(0) + 20 * N0 + 4 + 8 * n1, 3: 8 * n1 + 16 * N0}[kind]
+        alg = {1: bytes0, 2: mg.matrix_bytes(0) + 16 * N0 + 8 * n1, 3: 8 * n1 + 16 * N0}[kind]
         per_kernel[nm] = {"ms": t_ms, "GB/s": alg / (t_ms * 1e-3) / 1e9,
                           "frac": alg / (t_ms * 1e-3) / 1e9 / peak}
+    # bytes one V-cycle must move with the layouts in use
+    passes = 2 * smoother.n_iters if a.smoother == "jacobi" else 4 * smoother.n_iters
+    layout_bytes = 0
+    for l in range(levels - 1):
+        nl, nn = mg.get_n_dofs(l), mg.get_n_dofs(l + 1)
+        layout_bytes += (passes + 1) * (mg.matrix_bytes(l) + 24 * nl) + 24 * nl + 16 * nn
     vbytes = mg.vcycle_bytes()
 
     if rank != 0:
@@ -291,8 +305,10 @@ def run_b200(a):
                    "parallelism": "single GPU" if world == 1 else "replicas x%d" % world,
                    "mdof_per_s": vps * N0 / 1e6, "setup_s": setup_s,
                    "rss_after_timed_cycles": rss_after,
-                   "vcycle_algorithmic_bytes": vbytes,
-                   "vcycle_hbm_frac": vbytes / (ms / a.steps * 1e-3) / 1e9 / peak,
+                   "vcycle_layout_bytes": layout_bytes,
+                   "vcycle_hbm_frac": layout_bytes / (ms / a.steps * 1e-3) / 1e9 / peak,
+                   "vcycle_survey_formula_bytes": vbytes,
+                   "layouts": [mg.format(l) for l in range(levels)],
                    "kernels_level0": per_kernel},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
