@@ -72,6 +72,18 @@ SIGNATURES = {
     "amgb_hierarchy_create": (_i, [_i, _i, _pi, _pi, _pd, _pd, _l, C.POINTER(Options),
                                    C.POINTER(_p)]),
     "amgb_hierarchy_destroy": (_i, [_p]),
+    "amgb_comm_unique_id_bytes": (_i, []),
+    "amgb_comm_get_unique_id": (_i, [_p]),
+    "amgb_comm_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
+    "amgb_comm_destroy": (_i, [_p]),
+    "amgb_hierarchy_create_sharded": (_i, [_p, _l, _i, _i, _pi, _pi, _pd, _pd, _l, C.POINTER(Options),
+                                           C.POINTER(_p)]),
+    "amgb_hierarchy_n_sharded_levels": (_i, [_p]),
+    "amgb_hierarchy_local_range": (_i, [_p, _i, C.POINTER(_l), C.POINTER(_l)]),
+    "amgb_hierarchy_halo_exchanges_per_vcycle": (_l, [_p]),
+    "amgb_partition_plan": (_i, [_i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _pi, _i, _l,
+                                 C.POINTER(_i), np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
+                                 _pi, _pi, _pi]),
     "amgb_hierarchy_set_stream": (_i, [_p, _p]),
     "amgb_hierarchy_n_levels": (_i, [_p]),
     "amgb_hierarchy_n_dofs": (_l, [_p, _i]),
@@ -334,12 +346,47 @@ class MulticolorGaussSeidel(SmootherBase):
         _check(lib().amgb_smooth_color_gs(_mirror(A).h, u, _f64(b), self.n_iters))
 
 
+class Comm:
+    """One NCCL communicator per process (amgb_comm).  `exchange_id` is a callable that
+    takes rank 0's id bytes (or None on other ranks) and returns rank 0's bytes on every
+    rank -- e.g. a torch.distributed broadcast; the library itself never imports torch."""
+
+    def __init__(self, rank, world, exchange_id):
+        nbytes = lib().amgb_comm_unique_id_bytes()
+        buf = C.create_string_buffer(nbytes)
+        if rank == 0:
+            _check(lib().amgb_comm_get_unique_id(buf))
+        raw = exchange_id(buf.raw if rank == 0 else None)
+        buf = C.create_string_buffer(bytes(raw), nbytes)
+        h = _p()
+        _check(lib().amgb_comm_create(buf, rank, world, C.byref(h)))
+        self.h, self.rank, self.world = h, rank, world
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.amgb_comm_destroy(self.h)
+            self.h = None
+
+
+def partition_plan(level_sizes, half_bandwidth, world, min_rows_per_rank):
+    """Host-only: (n_sharded, starts[l][g], halo_lo, halo_hi, ghost) of the row-block plan."""
+    L = len(level_sizes)
+    sizes = np.ascontiguousarray(level_sizes, np.int64)
+    bw = _i32(half_bandwidth)
+    ns = _i()
+    starts = np.zeros(L * (world + 1), np.int64)
+    lo, hi, gh = np.zeros(L, np.int32), np.zeros(L, np.int32), np.zeros(L, np.int32)
+    _check(lib().amgb_partition_plan(L, sizes, bw, world, min_rows_per_rank, C.byref(ns), starts, lo, hi, gh))
+    k = ns.value
+    return k, starts.reshape(L, world + 1)[:k], lo[:k], hi[:k], gh[:k]
+
+
 class Multigrid:
     """AMG::Multigrid<double> (include/amg/multigrid.hpp:22-365) on the device."""
 
     def __init__(self, interpolator, smoother, A, b, n_levels, tolerance=1e-9,
                  compute_error_every_n_iters=10, n_iters=100, use_graph=True,
-                 skip_dead_coarse_smooth=True):
+                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18):
         self.interpolator, self.smoother = interpolator, smoother
         o = Options()
         lib().amgb_options_default(C.byref(o))
@@ -355,8 +402,14 @@ class Multigrid:
         o.skip_dead_coarse_smooth = int(skip_dead_coarse_smooth)
         b = _f64(b)
         h = _p()
-        _check(lib().amgb_hierarchy_create(A.rows, A.cols, A.colptr, A.rowidx, A.val, b, b.shape[0],
-                                           C.byref(o), C.byref(h)))
+        if comm is None:
+            _check(lib().amgb_hierarchy_create(A.rows, A.cols, A.colptr, A.rowidx, A.val, b, b.shape[0],
+                                               C.byref(o), C.byref(h)))
+        else:
+            _check(lib().amgb_hierarchy_create_sharded(comm.h, min_rows_per_rank, A.rows, A.cols, A.colptr,
+                                                       A.rowidx, A.val, b, b.shape[0], C.byref(o),
+                                                       C.byref(h)))
+        self.comm = comm
         self.h = h
         self.n_levels = n_levels
         self.display_error = False
@@ -481,6 +534,18 @@ class Multigrid:
         color = np.empty(self.get_n_dofs(level), np.int32)
         _check(lib().amgb_hierarchy_get_coloring(self.h, level, C.byref(nc), color))
         return nc.value, color
+
+    # ---- sharding ----
+    def n_sharded_levels(self):
+        return lib().amgb_hierarchy_n_sharded_levels(self.h)
+
+    def local_range(self, level):
+        b, e = _l(), _l()
+        _check(lib().amgb_hierarchy_local_range(self.h, level, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def halo_exchanges_per_vcycle(self):
+        return lib().amgb_hierarchy_halo_exchanges_per_vcycle(self.h)
 
     # ---- measurement helpers ----
     def set_stream(self, cuda_stream):

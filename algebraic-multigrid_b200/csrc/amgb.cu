@@ -17,6 +17,7 @@
 
 #include "host_setup.hpp"
 #include "kernels.cuh"
+#include "nccl_dyn.hpp"
 
 namespace {
 
@@ -38,6 +39,14 @@ struct ApiError : std::runtime_error {
     if (e_ != cudaSuccess)                                                                 \
       throw ApiError(AMGB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" + \
                                      __FILE__ + ":" + std::to_string(__LINE__) + ")");     \
+  } while (0)
+
+#define NCCL_CHECK(expr)                                                                  \
+  do {                                                                                    \
+    ncclResult_t r_ = (expr);                                                             \
+    if (r_ != ncclSuccess)                                                                \
+      throw ApiError(AMGB_ENCCL, std::string(#expr) + ": " + NcclApi::get().GetErrorString(r_) + \
+                                     " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")");   \
   } while (0)
 
 #define LAUNCH(kernel, grid, block, smem, stream, ...)            \
@@ -127,14 +136,15 @@ struct DevSell {
 };
 
 struct DevDia {
-  int n_rows = 0, n_cols = 0, ld = 0, n_diag = 0;
+  int n_rows = 0, c_min = 0, c_max = 0, ld = 0, n_diag = 0;
   int64_t nnz = 0;
   int off[dev::kMaxDiagDev] = {0};
   DevBuf<double> val;
   DevBuf<int> rows;
   void upload(const Dia& D, cudaStream_t s) {
     n_rows = D.n_rows;
-    n_cols = D.n_cols;
+    c_min = 0;
+    c_max = D.n_cols - 1;
     ld = D.ld;
     n_diag = D.n_diag;
     nnz = D.nnz;
@@ -146,7 +156,8 @@ struct DevDia {
   DiaView view() const {
     DiaView v;
     v.n_rows = n_rows;
-    v.n_cols = n_cols;
+    v.c_min = c_min;
+    v.c_max = c_max;
     v.ld = ld;
     v.n_diag = n_diag;
     for (int d = 0; d < dev::kMaxDiagDev; ++d) v.off[d] = off[d];
@@ -197,7 +208,9 @@ struct Operator {
   Csc M;                  // structural CSC exactly as handed in (explicit zeros kept)
   Csc MT;                 // transpose (rows of A); built once
   bool symmetric = true;  // M == MT bitwise
-  int n = 0;
+  int n = 0;              // rows this rank smooths (all rows, or the owned block)
+  int n_mat = 0;          // rows held on the device (n, or owned block + ghost rows)
+  bool block = false;     // true: device holds a row block with local numbering
   DevMat colrows;                   // row c = CSC column c (smoother.hpp:101-117)
   std::unique_ptr<DevMat> arows;    // rows of A when !symmetric
   // generic Gauss-Seidel fronts
@@ -213,7 +226,7 @@ struct Operator {
   void build(Csc&& A, cudaStream_t s) {
     if (A.rows != A.cols) throw std::invalid_argument("operator must be square");
     M = std::move(A);
-    n = M.cols;
+    n = n_mat = M.cols;
     MT = transpose(M);
     symmetric = bitwise_equal(M, MT);
     colrows.upload(M, nullptr, s);
@@ -222,7 +235,26 @@ struct Operator {
       arows->upload(MT, nullptr, s);
     }
   }
-  const DevMat& rows_of_A() const { return symmetric ? colrows : *arows; }
+  // Row-block mirror for a sharded level: rows [row_begin, row_begin + rows_stored) of A
+  // in DIA with local numbering; x is indexed relative to the first owned row, the
+  // halo-extended local vector allowing [-halo_lo, n_own + halo_hi - 1].
+  void build_block(Csc&& A, int row_begin, int rows_stored, int n_own, int halo_lo, int halo_hi,
+                   cudaStream_t s) {
+    if (A.rows != A.cols) throw std::invalid_argument("operator must be square");
+    M = std::move(A);
+    MT = transpose(M);
+    symmetric = bitwise_equal(M, MT);
+    block = true;
+    n = n_own;
+    n_mat = rows_stored;
+    Dia D = build_dia_block(host_rows_of_A(), row_begin, rows_stored);
+    if (!D.ok) throw std::invalid_argument("sharded levels need a banded operator (DIA layout)");
+    colrows.is_dia = true;
+    colrows.dia.upload(D, s);
+    colrows.dia.c_min = -halo_lo;
+    colrows.dia.c_max = n_own + halo_hi - 1;
+  }
+  const DevMat& rows_of_A() const { return (symmetric || block) ? colrows : *arows; }
   const Csc& host_rows_of_A() const { return symmetric ? M : MT; }  // CSC whose column k = row k of A
 
   void ensure_fronts(cudaStream_t s) {
@@ -255,6 +287,7 @@ struct Operator {
     if (!n) return;
     with_view(rows_of_A(), [&](auto V) {
       auto kern = dev::k_residual<decltype(V)>;
+      V.n_rows = n;
       LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, r);
     });
   }
@@ -262,6 +295,7 @@ struct Operator {
     if (!n) return;
     with_view(rows_of_A(), [&](auto V) {
       auto kern = dev::k_jacobi<decltype(V)>;
+      V.n_rows = n;
       LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, omega, out);
     });
   }
@@ -291,7 +325,8 @@ struct Operator {
                          int n_coarse, cudaStream_t s) const {
     with_view(rows_of_A(), [&](auto V) {
       auto kern = dev::k_residual_restrict<decltype(V)>;
-      LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, f_coarse, u_coarse, n_coarse);
+      V.n_rows = n_mat;
+      LAUNCH(kern, blocks_for(n_mat, 256), 256, 0, s, V, u, f, f_coarse, u_coarse, n_coarse);
     });
   }
   int rss_blocks() const { return std::max(1, blocks_for(n, 256)); }
@@ -300,6 +335,7 @@ struct Operator {
     const int nb = rss_blocks();
     with_view(rows_of_A(), [&](auto V) {
       auto kern = dev::k_rss_partial<decltype(V)>;
+      V.n_rows = n;
       LAUNCH(kern, nb, 256, 0, s, V, u, b, partial);
     });
     LAUNCH(dev::k_sum_partials, 1, 256, 0, s, partial, nb, out);
@@ -336,15 +372,43 @@ struct amgb_matrix {
 };
 
 // ============================================================================
+// amgb_comm: one NCCL communicator over the GPUs of one node (one rank per process)
+// ============================================================================
+struct amgb_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+  ~amgb_comm() {
+    if (comm) NcclApi::get().CommDestroy(comm);
+  }
+};
+
+// ============================================================================
 // amgb_hierarchy
 // ============================================================================
+// Per-level state.  A level is either whole on this GPU (single-GPU run, or an
+// agglomerated coarse level every rank keeps a replica of) or a contiguous row
+// block [s, e) of a sharded fine level, with halo_lo / halo_hi extra entries of u
+// below / above the block and `ghost` extra operator/rhs rows above it.
+struct LevelState {
+  bool sharded = false;
+  int64_t n_global = 0;
+  int64_t s = 0, e = 0;
+  int halo_lo = 0, halo_hi = 0;
+  int n_own = 0;  // e - s
+  int n_mat = 0;  // operator / rhs rows held: n_own (+ ghost rows, clipped at the last row)
+  DevBuf<double> u, f, tmp;
+  double* u_own() const { return u.p + halo_lo; }
+  double* tmp_own() const { return tmp.p + halo_lo; }
+  int64_t n_vec() const { return (int64_t)halo_lo + n_own + halo_hi; }
+};
+
 struct amgb_hierarchy {
   int device = 0;
   amgb_options opt{};
   int L = 0;
   std::vector<int64_t> n;
   std::vector<std::unique_ptr<Operator>> ops;
-  std::vector<DevBuf<double>> u, f, tmp;
+  std::vector<LevelState> lv;
   DevBuf<double> partial, scalar;
   BandedLdlt factor;
   DevBuf<double> dL, dd, dwork;
@@ -356,51 +420,120 @@ struct amgb_hierarchy {
   bool ldlt_attr_set = false;
   int64_t iters_done = 0;
   std::vector<double> history;
+  // sharding
+  amgb_comm* comm = nullptr;  // borrowed
+  PartitionPlan plan;
+  int n_sharded = 0;
+  int64_t halo_exchanges_per_vcycle = 0;
 
   ~amgb_hierarchy() {
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
+  int rank() const { return comm ? comm->rank : 0; }
+  int world() const { return comm ? comm->world : 1; }
 
   void prepare_smoother(int l) {
+    if (lv[l].sharded) {
+      if (opt.smoother != AMGB_SMOOTHER_JACOBI)
+        throw std::invalid_argument("sharded levels support the damped-Jacobi smoother only");
+      return;
+    }
     if (opt.smoother == AMGB_SMOOTHER_GS) ops[l]->ensure_fronts(stream);
     if (opt.smoother == AMGB_SMOOTHER_COLOR_GS) ops[l]->ensure_colors(stream);
+  }
+
+  // Halo exchange of a halo-extended level vector with ranks g-1 / g+1: one grouped
+  // NCCL send/recv pair per neighbour on the compute stream.
+  void exchange(int l, double* base, cudaStream_t s) {
+    const LevelState& S = lv[l];
+    if (!S.sharded) return;
+    NcclApi& nc = NcclApi::get();
+    const int g = rank(), G = world();
+    const int up_cnt = plan.halo_hi[l];  // what rank g-1 keeps above its block = my first rows
+    const int dn_cnt = plan.halo_lo[l];  // what rank g+1 keeps below its block = my last rows
+    NCCL_CHECK(nc.GroupStart());
+    if (g > 0) {
+      NCCL_CHECK(nc.Send(base + S.halo_lo, up_cnt, ncclDouble, g - 1, comm->comm, s));
+      NCCL_CHECK(nc.Recv(base, S.halo_lo, ncclDouble, g - 1, comm->comm, s));
+    }
+    if (g + 1 < G) {
+      NCCL_CHECK(nc.Send(base + S.halo_lo + S.n_own - dn_cnt, dn_cnt, ncclDouble, g + 1, comm->comm, s));
+      NCCL_CHECK(nc.Recv(base + S.halo_lo + S.n_own, S.halo_hi, ncclDouble, g + 1, comm->comm, s));
+    }
+    NCCL_CHECK(nc.GroupEnd());
+    ++halo_exchanges_per_vcycle;
+  }
+  // every rank contributes its block [start[r], start[r+1]) of a full-length vector
+  void allgather_blocks(double* full, const std::vector<int64_t>& start, cudaStream_t s) {
+    NcclApi& nc = NcclApi::get();
+    NCCL_CHECK(nc.GroupStart());
+    for (int r = 0; r < world(); ++r) {
+      const int64_t cnt = start[r + 1] - start[r];
+      if (cnt > 0)
+        NCCL_CHECK(nc.Broadcast(full + start[r], full + start[r], (size_t)cnt, ncclDouble, r, comm->comm, s));
+    }
+    NCCL_CHECK(nc.GroupEnd());
   }
 
   // smoother->smooth(A_l, u_l, f_l)   (multigrid.hpp:268-269, :300-301)
   void smooth(int l, cudaStream_t s) {
     Operator& A = *ops[l];
+    LevelState& S = lv[l];
     const int64_t iters = opt.smoother_iters;
     if (opt.smoother == AMGB_SMOOTHER_GS) {
       for (int64_t it = 0; it < iters; ++it) {  // smoother.hpp:195-198
-        A.gs_forward(f[l].p, u[l].p, s);
-        A.gs_backward(f[l].p, u[l].p, s);
+        A.gs_forward(S.f.p, S.u.p, s);
+        A.gs_backward(S.f.p, S.u.p, s);
       }
     } else if (opt.smoother == AMGB_SMOOTHER_JACOBI) {
-      double* src = u[l].p;
-      double* dst = tmp[l].p;
+      double* src = S.u.p;
+      double* dst = S.tmp.p;
       for (int64_t it = 0; it < iters; ++it) {
-        A.jacobi(src, f[l].p, opt.omega, dst, s);
+        exchange(l, src, s);
+        A.jacobi(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, s);
         std::swap(src, dst);
       }
-      if (src != u[l].p)
-        CUDA_CHECK(cudaMemcpyAsync(u[l].p, src, sizeof(double) * n[l], cudaMemcpyDeviceToDevice, s));
+      if (src != S.u.p)
+        CUDA_CHECK(cudaMemcpyAsync(S.u_own(), src + S.halo_lo, sizeof(double) * S.n_own,
+                                   cudaMemcpyDeviceToDevice, s));
     } else {
       for (int64_t it = 0; it < iters; ++it) {
-        for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, f[l].p, u[l].p, s);
-        for (int c = A.n_colors - 1; c >= 0; --c) A.color_pass(c, f[l].p, u[l].p, s);
+        for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, S.f.p, S.u.p, s);
+        for (int c = A.n_colors - 1; c >= 0; --c) A.color_pass(c, S.f.p, S.u.p, s);
       }
     }
   }
   // f_{l+1} = R_l (f_l - A_l u_l), u_{l+1} = 0   (multigrid.hpp:272-282)
   void residual_restrict(int l, cudaStream_t s) {
-    ops[l]->residual_restrict(u[l].p, f[l].p, f[l + 1].p, u[l + 1].p, (int)n[l + 1], s);
+    LevelState& F = lv[l];
+    LevelState& C = lv[l + 1];
+    if (!F.sharded) {
+      ops[l]->residual_restrict(F.u.p, F.f.p, C.f.p, C.u.p, (int)n[l + 1], s);
+      return;
+    }
+    exchange(l, F.u.p, s);
+    CUDA_CHECK(cudaMemsetAsync(C.u.p, 0, sizeof(double) * C.u.n, s));
+    if (C.sharded) {
+      ops[l]->residual_restrict(F.u_own(), F.f.p, C.f.p, C.u_own(), C.n_mat, s);
+    } else {
+      // first agglomerated level: every rank writes its coarse block straight into the
+      // full-length rhs, then the blocks are exchanged so each rank holds a replica
+      const std::vector<int64_t>& cs = coarse_block_start;
+      const int64_t c0 = cs[rank()], c1 = cs[rank() + 1];
+      ops[l]->residual_restrict(F.u_own(), F.f.p, C.f.p + c0, C.u.p + c0, (int)(c1 - c0), s);
+      allgather_blocks(C.f.p, cs, s);
+    }
   }
   // u_l = u_l + P_l u_{l+1}   (multigrid.hpp:294-296)
   void prolong_add(int l, cudaStream_t s) {
-    LAUNCH(dev::k_prolong_add, blocks_for(n[l], 256), 256, 0, s, u[l + 1].p, (int)n[l + 1], u[l].p,
-           (int)n[l]);
+    LevelState& F = lv[l];
+    LevelState& C = lv[l + 1];
+    if (C.sharded) exchange(l + 1, C.u.p, s);  // needs e[s_c - 1]
+    const int e_first = C.sharded ? (int)(C.s - C.halo_lo) : 0;
+    LAUNCH(dev::k_prolong_add, blocks_for(F.n_own, 256), 256, 0, s, C.u.p, e_first, (int)n[l + 1],
+           F.u_own(), (int)F.s, F.n_own);
   }
   void coarse_solve(cudaStream_t s) {  // multigrid.hpp:287-288
     const int nc = factor.n, bw = factor.bw;
@@ -416,10 +549,13 @@ struct amgb_hierarchy {
                                       (int)cap));
       ldlt_attr_set = true;
     }
-    LAUNCH(dev::k_banded_ldlt_solve, 1, threads, smem, s, dL.p, dd.p, nc, bw, f[L - 1].p, u[L - 1].p,
+    LAUNCH(dev::k_banded_ldlt_solve, 1, threads, smem, s, dL.p, dd.p, nc, bw, lv[L - 1].f.p, lv[L - 1].u.p,
            dwork.p, x_smem, l_smem);
   }
+  std::vector<int64_t> coarse_block_start;  // block starts of level n_sharded (image of the fine blocks)
+
   void enqueue_vcycle(cudaStream_t s) {
+    halo_exchanges_per_vcycle = 0;
     for (int l = 0; l < L; ++l) {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
@@ -462,24 +598,75 @@ struct amgb_hierarchy {
       launches_per_vcycle = g_launches.load() - before;
     }
   }
-  double rss() {
-    ops[0]->rss(u[0].p, f[0].p, partial.p, scalar.p, stream);
+  // sum over all ranks of a device scalar, returned on the host
+  double finish_scalar() {
+    if (comm && world() > 1)
+      NCCL_CHECK(NcclApi::get().AllReduce(scalar.p, scalar.p, 1, ncclDouble, ncclSum, comm->comm, stream));
     double out = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(&out, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
     return out;
   }
-  double sumsq(const double* x, int64_t count) {
-    const int nb = std::max(1, blocks_for(count, 256));
-    LAUNCH(dev::k_sumsq_partial, nb, 256, 0, stream, x, (int)count, partial.p);
-    LAUNCH(dev::k_sum_partials, 1, 256, 0, stream, partial.p, nb, scalar.p);
+  double rss() {
+    LevelState& S = lv[0];
+    if (S.sharded) exchange(0, S.u.p, stream);
+    ops[0]->rss(S.u_own(), S.f.p, partial.p, scalar.p, stream);
+    return S.sharded ? finish_scalar() : finish_scalar_local();
+  }
+  double finish_scalar_local() {
     double out = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(&out, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
     return out;
+  }
+  // sum of squares of the level-0 rhs
+  double rhs_sumsq() {
+    LevelState& S = lv[0];
+    const int nb = std::max(1, blocks_for(S.n_own, 256));
+    LAUNCH(dev::k_sumsq_partial, nb, 256, 0, stream, S.f.p, S.n_own, partial.p);
+    LAUNCH(dev::k_sum_partials, 1, 256, 0, stream, partial.p, nb, scalar.p);
+    return S.sharded ? finish_scalar() : finish_scalar_local();
   }
   void check_level(int l, bool need_next = false) const {
     if (l < 0 || l >= L || (need_next && l + 1 >= L)) throw std::invalid_argument("level out of range");
+  }
+  void require_whole(int l) const {
+    if (lv[l].sharded)
+      throw ApiError(AMGB_ESTATE, "this per-operator entry point is not available on a sharded level");
+  }
+
+  // ---- host <-> device copies of a level vector given / returned at full length ----
+  void upload_u(int l, const double* full) {
+    LevelState& S = lv[l];
+    if (!S.sharded) {
+      CUDA_CHECK(cudaMemcpyAsync(S.u.p, full, sizeof(double) * n[l], cudaMemcpyHostToDevice, stream));
+    } else {
+      const int64_t lo = std::max<int64_t>(0, S.s - S.halo_lo), hi = std::min<int64_t>(n[l], S.e + S.halo_hi);
+      CUDA_CHECK(cudaMemcpyAsync(S.u.p + (lo - (S.s - S.halo_lo)), full + lo, sizeof(double) * (hi - lo),
+                                 cudaMemcpyHostToDevice, stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+  void upload_f(int l, const double* full) {
+    LevelState& S = lv[l];
+    CUDA_CHECK(cudaMemcpyAsync(S.f.p, full + S.s, sizeof(double) * S.n_mat, cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+  void download(int l, bool want_u, double* full) {
+    LevelState& S = lv[l];
+    if (!S.sharded) {
+      CUDA_CHECK(cudaMemcpyAsync(full, want_u ? S.u.p : S.f.p, sizeof(double) * n[l],
+                                 cudaMemcpyDeviceToHost, stream));
+    } else {
+      DevBuf<double> whole;
+      whole.alloc(n[l]);
+      CUDA_CHECK(cudaMemcpyAsync(whole.p + S.s, want_u ? S.u_own() : S.f.p, sizeof(double) * S.n_own,
+                                 cudaMemcpyDeviceToDevice, stream));
+      allgather_blocks(whole.p, plan.start[l], stream);
+      CUDA_CHECK(cudaMemcpyAsync(full, whole.p, sizeof(double) * n[l], cudaMemcpyDeviceToHost, stream));
+      CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream));
   }
 };
 
@@ -671,86 +858,204 @@ void amgb_options_default(amgb_options* opt) {
   if (opt) options_default(opt);
 }
 
+static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_rows, int n_cols,
+                             const int* colptr, const int* rowidx, const double* val, const double* b,
+                             int64_t b_rows, const amgb_options* opt_in, amgb_hierarchy** out) {
+  if (!out || !opt_in || !colptr) throw std::invalid_argument("null argument");
+  const amgb_options& o = *opt_in;
+  // multigrid.hpp:165-178 -- same order, same messages
+  if (o.compute_error_every_n_iters > o.n_iters)
+    throw std::invalid_argument("`compute_error_every_n_iters` must be leq to `n_iters`, got " +
+                                std::to_string(o.compute_error_every_n_iters) + " and " +
+                                std::to_string(o.n_iters));
+  if ((int64_t)n_rows != b_rows)
+    throw std::invalid_argument("`A` and `b` must have the same number of degrees of freedom, got " +
+                                std::to_string(n_rows) + " and " + std::to_string(b_rows));
+  if (o.n_levels < 1) throw std::invalid_argument("n_levels must be >= 1");
+  if (n_rows != n_cols) throw std::invalid_argument("A must be square");
+  if (o.smoother < 0 || o.smoother > 2) throw std::invalid_argument("unknown smoother kind");
+  if (!b || !rowidx || !val) throw std::invalid_argument("null argument");
+  require_device();
+
+  std::unique_ptr<amgb_hierarchy> h(new amgb_hierarchy());
+  h->opt = o;
+  h->L = o.n_levels;
+  h->comm = comm;
+  CUDA_CHECK(cudaGetDevice(&h->device));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  cudaStream_t s = h->stream;
+  const int L = h->L;
+
+  // ---- host hierarchy (multigrid.hpp:190-223): every rank builds all of it ----
+  std::vector<Csc> mats(L);
+  mats[0] = csc_from_arrays(n_rows, n_cols, colptr, rowidx, val);
+  h->n.resize(L);
+  h->n[0] = n_rows;
+  for (int l = 1; l < L; ++l) {
+    const int64_t nh = h->n[l - 1];
+    const int64_t nH = coarse_dofs(nh);
+    if (nH < 1) throw std::invalid_argument("too many levels: level " + std::to_string(l) + " is empty");
+    Csc P = make_prolongation(nh, nH);
+    Csc R = transpose(P);
+    mats[l] = galerkin(R, mats[l - 1], P);
+    h->n[l] = nH;
+  }
+  // coarsest factorisation (multigrid.hpp:240-243); the direct solve is a banded
+  // substitution in one block, so refuse hierarchies whose coarsest level is not small
+  std::vector<int> half_bw(L, 0);
+  for (int l = 0; l < L; ++l)
+    for (int c = 0; c < mats[l].cols; ++c)
+      for (int p = mats[l].colptr[c]; p < mats[l].colptr[c + 1]; ++p)
+        if (mats[l].val[p] != 0.0) half_bw[l] = std::max(half_bw[l], std::abs(mats[l].rowidx[p] - c));
+  {
+    const int64_t nc = h->n[L - 1], bw = std::max(half_bw[L - 1], 1);
+    if ((double)nc * bw * bw > 2e10 || nc * bw > (1ll << 27))
+      throw std::invalid_argument("coarsest level too large for the direct solve (" + std::to_string(nc) +
+                                  " DOF, half-bandwidth " + std::to_string(bw) + "): use more levels");
+  }
+  h->factor = factor_banded_ldlt(mats[L - 1]);
+
+  // ---- partition (sharded runs only) ----
+  const int world = comm ? comm->world : 1;
+  if (world > 1) {
+    if (o.smoother != AMGB_SMOOTHER_JACOBI)
+      throw std::invalid_argument("the row-block sharded V-cycle supports the damped-Jacobi smoother only "
+                                  "(lexicographic Gauss-Seidel is a single-GPU path)");
+    h->plan = make_partition_plan(h->n, half_bw, world, min_rows_per_rank);
+    h->n_sharded = h->plan.n_sharded;
+    if (h->n_sharded > 0) {
+      h->coarse_block_start.resize(world + 1);
+      for (int g = 0; g <= world; ++g)
+        h->coarse_block_start[g] = (g == world) ? h->n[h->n_sharded] : h->plan.start[h->n_sharded - 1][g] / 2;
+    }
+  }
+
+  // ---- device mirrors ----
+  h->ops.resize(L);
+  h->lv.resize(L);
+  const int g = comm ? comm->rank : 0;
+  for (int l = 0; l < L; ++l) {
+    LevelState& S = h->lv[l];
+    S.n_global = h->n[l];
+    h->ops[l].reset(new Operator());
+    if (l < h->n_sharded) {
+      S.sharded = true;
+      S.s = h->plan.start[l][g];
+      S.e = h->plan.start[l][g + 1];
+      S.halo_lo = h->plan.halo_lo[l];
+      S.halo_hi = h->plan.halo_hi[l];
+      S.n_own = (int)(S.e - S.s);
+      S.n_mat = (int)std::min<int64_t>(S.n_own + h->plan.ghost[l], h->n[l] - S.s);
+      h->ops[l]->build_block(std::move(mats[l]), (int)S.s, S.n_mat, S.n_own, S.halo_lo, S.halo_hi, s);
+    } else {
+      S.s = 0;
+      S.e = h->n[l];
+      S.n_own = S.n_mat = (int)h->n[l];
+      h->ops[l]->build(std::move(mats[l]), s);
+    }
+    S.u.alloc(S.n_vec());
+    S.u.zero(s);
+    S.f.alloc(S.n_mat);
+    S.f.zero(s);
+    if (o.smoother == AMGB_SMOOTHER_JACOBI) {
+      S.tmp.alloc(S.n_vec());
+      S.tmp.zero(s);
+    }
+    if (!(l + 1 == L && o.skip_dead_coarse_smooth)) h->prepare_smoother(l);
+  }
+  h->upload_f(0, b);
+  h->partial.alloc(std::max(1, blocks_for(h->lv[0].n_own, 256)));
+  h->scalar.alloc(1);
+  h->dL.upload(h->factor.L, s);
+  h->dd.upload(h->factor.d, s);
+  h->dwork.alloc(h->factor.n);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  *out = h.release();
+}
+
 int amgb_hierarchy_create(int n_rows, int n_cols, const int* colptr, const int* rowidx, const double* val,
                           const double* b, int64_t b_rows, const amgb_options* opt_in,
                           amgb_hierarchy** out) {
   return guarded([&] {
-    if (!out || !opt_in || !colptr) throw std::invalid_argument("null argument");
-    const amgb_options& o = *opt_in;
-    // multigrid.hpp:165-178 -- same order, same messages
-    if (o.compute_error_every_n_iters > o.n_iters)
-      throw std::invalid_argument("`compute_error_every_n_iters` must be leq to `n_iters`, got " +
-                                  std::to_string(o.compute_error_every_n_iters) + " and " +
-                                  std::to_string(o.n_iters));
-    if ((int64_t)n_rows != b_rows)
-      throw std::invalid_argument("`A` and `b` must have the same number of degrees of freedom, got " +
-                                  std::to_string(n_rows) + " and " + std::to_string(b_rows));
-    if (o.n_levels < 1) throw std::invalid_argument("n_levels must be >= 1");
-    if (n_rows != n_cols) throw std::invalid_argument("A must be square");
-    if (o.smoother < 0 || o.smoother > 2) throw std::invalid_argument("unknown smoother kind");
-    if (!b || !rowidx || !val) throw std::invalid_argument("null argument");
-    require_device();
-
-    std::unique_ptr<amgb_hierarchy> h(new amgb_hierarchy());
-    h->opt = o;
-    h->L = o.n_levels;
-    CUDA_CHECK(cudaGetDevice(&h->device));
-    CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    h->stream = h->own_stream;
-    cudaStream_t s = h->stream;
-
-    h->n.resize(h->L);
-    h->ops.resize(h->L);
-    h->u.resize(h->L);
-    h->f.resize(h->L);
-    h->tmp.resize(h->L);
-
-    // level 0 (multigrid.hpp:190-204)
-    Csc A = csc_from_arrays(n_rows, n_cols, colptr, rowidx, val);
-    for (int l = 0; l < h->L; ++l) {
-      if (l > 0) {
-        // multigrid.hpp:211-223
-        const Csc& Ah = h->ops[l - 1]->M;
-        const int64_t nh = h->n[l - 1];
-        const int64_t nH = coarse_dofs(nh);
-        if (nH < 1) throw std::invalid_argument("too many levels: level " + std::to_string(l) + " is empty");
-        Csc P = make_prolongation(nh, nH);
-        Csc R = transpose(P);
-        A = galerkin(R, Ah, P);
-      }
-      h->n[l] = A.cols;
-      h->ops[l].reset(new Operator());
-      h->ops[l]->build(std::move(A), s);
-      h->u[l].alloc(h->n[l]);
-      h->u[l].zero(s);
-      h->f[l].alloc(h->n[l]);
-      if (l == 0) h->f[l].upload(b, h->n[0], s);
-      else h->f[l].zero(s);
-      if (o.smoother == AMGB_SMOOTHER_JACOBI) h->tmp[l].alloc(h->n[l]);
-      if (!(l + 1 == h->L && o.skip_dead_coarse_smooth)) h->prepare_smoother(l);
-    }
-    h->partial.alloc(std::max(1, blocks_for(h->n[0], 256)));
-    h->scalar.alloc(1);
-    // coarsest factorisation (multigrid.hpp:240-243); the direct solve is a banded
-    // substitution in one block, so refuse hierarchies whose coarsest level is not small
-    {
-      const Csc& Ac = h->ops[h->L - 1]->M;
-      int64_t bw = 0;
-      for (int c = 0; c < Ac.cols; ++c)
-        for (int p = Ac.colptr[c]; p < Ac.colptr[c + 1]; ++p) bw = std::max<int64_t>(bw, Ac.rowidx[p] - c);
-      if ((double)Ac.cols * (double)bw * (double)bw > 2e10 || (int64_t)Ac.cols * std::max<int64_t>(bw, 1) > (1ll << 27))
-        throw std::invalid_argument("coarsest level too large for the direct solve (" +
-                                    std::to_string(Ac.cols) + " DOF, half-bandwidth " +
-                                    std::to_string(bw) + "): use more levels");
-    }
-    h->factor = factor_banded_ldlt(h->ops[h->L - 1]->M);
-    h->dL.upload(h->factor.L, s);
-    h->dd.upload(h->factor.d, s);
-    h->dwork.alloc(h->factor.n);
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    *out = h.release();
+    create_hierarchy(nullptr, 0, n_rows, n_cols, colptr, rowidx, val, b, b_rows, opt_in, out);
   });
 }
+int amgb_hierarchy_create_sharded(amgb_comm* comm, int64_t min_rows_per_rank, int n_rows, int n_cols,
+                                  const int* colptr, const int* rowidx, const double* val, const double* b,
+                                  int64_t b_rows, const amgb_options* opt_in, amgb_hierarchy** out) {
+  return guarded([&] {
+    if (!comm) throw std::invalid_argument("null communicator");
+    CUDA_CHECK(cudaSetDevice(comm->device));
+    create_hierarchy(comm, std::max<int64_t>(min_rows_per_rank, 1), n_rows, n_cols, colptr, rowidx, val, b,
+                     b_rows, opt_in, out);
+  });
+}
+int amgb_hierarchy_n_sharded_levels(const amgb_hierarchy* h) { return h ? h->n_sharded : 0; }
+int amgb_hierarchy_local_range(const amgb_hierarchy* h, int level, int64_t* begin, int64_t* end) {
+  return guarded([&] {
+    if (!h) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    if (begin) *begin = h->lv[level].s;
+    if (end) *end = h->lv[level].e;
+  });
+}
+int64_t amgb_hierarchy_halo_exchanges_per_vcycle(const amgb_hierarchy* h) {
+  return h ? h->halo_exchanges_per_vcycle : 0;
+}
+
+// ---- communicator ----
+int amgb_comm_unique_id_bytes(void) { return (int)sizeof(ncclUniqueId); }
+int amgb_comm_get_unique_id(void* id) {
+  return guarded([&] {
+    if (!id) throw std::invalid_argument("null argument");
+    ncclUniqueId u;
+    NCCL_CHECK(NcclApi::get().GetUniqueId(&u));
+    std::memcpy(id, &u, sizeof(u));
+  });
+}
+int amgb_comm_create(const void* id, int rank, int world, amgb_comm** out) {
+  return guarded([&] {
+    if (!id || !out || world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad communicator arguments");
+    require_device();
+    std::unique_ptr<amgb_comm> c(new amgb_comm());
+    c->rank = rank;
+    c->world = world;
+    CUDA_CHECK(cudaGetDevice(&c->device));
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    NCCL_CHECK(NcclApi::get().CommInitRank(&c->comm, world, u, rank));
+    *out = c.release();
+  });
+}
+int amgb_comm_destroy(amgb_comm* c) {
+  return guarded([&] {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    delete c;
+  });
+}
+// host-only: the row-block plan a sharded hierarchy would use
+int amgb_partition_plan(int n_levels, const int64_t* level_sizes, const int* half_bandwidth, int world,
+                        int64_t min_rows_per_rank, int* n_sharded, int64_t* starts, int* halo_lo,
+                        int* halo_hi, int* ghost) {
+  return guarded([&] {
+    if (!level_sizes || !half_bandwidth || !n_sharded || n_levels < 1 || world < 1)
+      throw std::invalid_argument("bad plan arguments");
+    std::vector<int64_t> sizes(level_sizes, level_sizes + n_levels);
+    std::vector<int> bw(half_bandwidth, half_bandwidth + n_levels);
+    PartitionPlan P = make_partition_plan(sizes, bw, world, std::max<int64_t>(min_rows_per_rank, 1));
+    *n_sharded = P.n_sharded;
+    for (int l = 0; l < P.n_sharded; ++l) {
+      if (starts)
+        for (int g = 0; g <= world; ++g) starts[(size_t)l * (world + 1) + g] = P.start[l][g];
+      if (halo_lo) halo_lo[l] = P.halo_lo[l];
+      if (halo_hi) halo_hi[l] = P.halo_hi[l];
+      if (ghost) ghost[l] = P.ghost[l];
+    }
+  });
+}
+
 int amgb_hierarchy_destroy(amgb_hierarchy* h) {
   return guarded([&] {
     if (!h) return;
@@ -787,29 +1092,37 @@ int amgb_hierarchy_get_matrix(const amgb_hierarchy* h, int level, int* colptr, i
     if (val) std::memcpy(val, M.val.data(), M.val.size() * sizeof(double));
   });
 }
-static int copy_level_vec(amgb_hierarchy* h, int level, std::vector<DevBuf<double>>& v, double* host,
-                          const double* src) {
+int amgb_hierarchy_get_soln(amgb_hierarchy* h, int level, double* u) {
   return guarded([&] {
-    if (!h || (!host && !src)) throw std::invalid_argument("null argument");
+    if (!h || !u) throw std::invalid_argument("null argument");
     h->check_level(level);
     CUDA_CHECK(cudaSetDevice(h->device));
-    if (host) v[level].download(host, h->stream);
-    else CUDA_CHECK(cudaMemcpyAsync(v[level].p, src, sizeof(double) * h->n[level], cudaMemcpyHostToDevice,
-                                    h->stream));
-    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->download(level, true, u);
   });
 }
-int amgb_hierarchy_get_soln(amgb_hierarchy* h, int level, double* u) {
-  return copy_level_vec(h, level, h->u, u, nullptr);
-}
 int amgb_hierarchy_get_rhs(amgb_hierarchy* h, int level, double* f) {
-  return copy_level_vec(h, level, h->f, f, nullptr);
+  return guarded([&] {
+    if (!h || !f) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->download(level, false, f);
+  });
 }
 int amgb_hierarchy_set_soln(amgb_hierarchy* h, int level, const double* u) {
-  return copy_level_vec(h, level, h->u, nullptr, u);
+  return guarded([&] {
+    if (!h || !u) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->upload_u(level, u);
+  });
 }
 int amgb_hierarchy_set_rhs(amgb_hierarchy* h, int level, const double* f) {
-  return copy_level_vec(h, level, h->f, nullptr, f);
+  return guarded([&] {
+    if (!h || !f) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->upload_f(level, f);
+  });
 }
 int amgb_hierarchy_get_coloring(const amgb_hierarchy* h, int level, int* n_colors, int* color) {
   return guarded([&] {
@@ -871,7 +1184,7 @@ int amgb_solve_relative(amgb_hierarchy* h, double rel_tol, int64_t* iters_done, 
   return guarded([&] {
     if (!h) throw std::invalid_argument("null argument");
     CUDA_CHECK(cudaSetDevice(h->device));
-    const double bnorm2 = h->sumsq(h->f[0].p, h->n[0]);
+    const double bnorm2 = h->rhs_sumsq();
     int64_t iter = 0;
     double rel = INFINITY;
     h->history.clear();
@@ -908,6 +1221,7 @@ int amgb_restrict(amgb_hierarchy* h, int level, const double* r_fine, double* f_
   return guarded([&] {
     if (!h || !r_fine || !f_coarse) throw std::invalid_argument("null argument");
     h->check_level(level, true);
+    h->require_whole(level);
     CUDA_CHECK(cudaSetDevice(h->device));
     DevBuf<double> r, fc;
     r.upload(r_fine, h->n[level], h->stream);
@@ -922,12 +1236,13 @@ int amgb_prolong_add(amgb_hierarchy* h, int level, const double* e_coarse, doubl
   return guarded([&] {
     if (!h || !e_coarse || !u_fine) throw std::invalid_argument("null argument");
     h->check_level(level, true);
+    h->require_whole(level);
     CUDA_CHECK(cudaSetDevice(h->device));
     DevBuf<double> e, uf;
     e.upload(e_coarse, h->n[level + 1], h->stream);
     uf.upload(u_fine, h->n[level], h->stream);
-    LAUNCH(dev::k_prolong_add, blocks_for(h->n[level], 256), 256, 0, h->stream, e.p, (int)h->n[level + 1],
-           uf.p, (int)h->n[level]);
+    LAUNCH(dev::k_prolong_add, blocks_for(h->n[level], 256), 256, 0, h->stream, e.p, 0, (int)h->n[level + 1],
+           uf.p, 0, (int)h->n[level]);
     uf.download(u_fine, h->stream);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   });
@@ -938,7 +1253,6 @@ int amgb_smooth_level(amgb_hierarchy* h, int level) {
     h->check_level(level);
     CUDA_CHECK(cudaSetDevice(h->device));
     h->prepare_smoother(level);
-    if (h->opt.smoother == AMGB_SMOOTHER_JACOBI && !h->tmp[level].p) h->tmp[level].alloc(h->n[level]);
     h->smooth(level, h->stream);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   });
@@ -947,10 +1261,11 @@ int amgb_residual_level(amgb_hierarchy* h, int level, double* r) {
   return guarded([&] {
     if (!h || !r) throw std::invalid_argument("null argument");
     h->check_level(level);
+    h->require_whole(level);
     CUDA_CHECK(cudaSetDevice(h->device));
     DevBuf<double> rd;
     rd.alloc(h->n[level]);
-    h->ops[level]->residual(h->u[level].p, h->f[level].p, rd.p, h->stream);
+    h->ops[level]->residual(h->lv[level].u.p, h->lv[level].f.p, rd.p, h->stream);
     rd.download(r, h->stream);
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
   });
@@ -1009,15 +1324,17 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
   return guarded([&] {
     if (!h || !ms_out || reps < 1) throw std::invalid_argument("bad argument");
     h->check_level(level, kind >= 2);
+    if (kind >= 2) h->require_whole(level);
     CUDA_CHECK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     h->prepare_smoother(level);
-    if (!h->tmp[level].p) h->tmp[level].alloc(h->n[level]);
     Operator& A = *h->ops[level];
+    LevelState& S = h->lv[level];
+    if (!S.tmp.p) S.tmp.alloc(S.n_vec());
     DevBuf<double> scratch_u, scratch_c, scratch_c2;
-    scratch_u.alloc(h->n[level]);
-    CUDA_CHECK(cudaMemcpyAsync(scratch_u.p, h->u[level].p, sizeof(double) * h->n[level],
-                               cudaMemcpyDeviceToDevice, s));
+    scratch_u.alloc(S.n_vec());
+    CUDA_CHECK(cudaMemcpyAsync(scratch_u.p, S.u.p, sizeof(double) * S.n_vec(), cudaMemcpyDeviceToDevice, s));
+    double* su = scratch_u.p + S.halo_lo;  // first owned row (no halo exchange is timed here)
     if (kind >= 2) {
       scratch_c.alloc(h->n[level + 1]);
       scratch_c.zero(s);
@@ -1027,21 +1344,21 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
       switch (kind) {
         case 0:
           if (h->opt.smoother == AMGB_SMOOTHER_JACOBI)
-            A.jacobi(scratch_u.p, h->f[level].p, h->opt.omega, h->tmp[level].p, s);
+            A.jacobi(su, S.f.p, h->opt.omega, S.tmp_own(), s);
           else if (h->opt.smoother == AMGB_SMOOTHER_COLOR_GS)
-            for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, h->f[level].p, scratch_u.p, s);
+            for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, S.f.p, scratch_u.p, s);
           else
-            A.gs_forward(h->f[level].p, scratch_u.p, s);
+            A.gs_forward(S.f.p, scratch_u.p, s);
           break;
         case 1:
-          A.residual(scratch_u.p, h->f[level].p, h->tmp[level].p, s);
+          A.residual(su, S.f.p, S.tmp_own(), s);
           break;
         case 2:
-          A.residual_restrict(scratch_u.p, h->f[level].p, scratch_c2.p, scratch_c.p, (int)h->n[level + 1], s);
+          A.residual_restrict(scratch_u.p, S.f.p, scratch_c2.p, scratch_c.p, (int)h->n[level + 1], s);
           break;
         case 3:
-          LAUNCH(dev::k_prolong_add, blocks_for(h->n[level], 256), 256, 0, s, scratch_c.p,
-                 (int)h->n[level + 1], scratch_u.p, (int)h->n[level]);
+          LAUNCH(dev::k_prolong_add, blocks_for(h->n[level], 256), 256, 0, s, scratch_c.p, 0,
+                 (int)h->n[level + 1], scratch_u.p, 0, (int)h->n[level]);
           break;
         default:
           throw std::invalid_argument("unknown kernel kind");

@@ -333,6 +333,61 @@ Dia build_dia(const Csc& M, const std::vector<int>* rows) {
   return D;
 }
 
+Dia build_dia_block(const Csc& M, int row_begin, int n_rows) {
+  std::vector<int> rows(n_rows);
+  for (int t = 0; t < n_rows; ++t) rows[t] = row_begin + t;
+  Dia D = build_dia(M, &rows);
+  D.rows.clear();  // local numbering: row t of the block is thread t
+  return D;
+}
+
+// ------------------------------------------------------------------ partition plan
+
+PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
+                                  const std::vector<int>& half_bandwidth, int world,
+                                  int64_t min_rows_per_rank) {
+  PartitionPlan P;
+  P.world = world;
+  P.n_levels = static_cast<int>(level_sizes.size());
+  P.n = level_sizes;
+  if (world <= 1) return P;
+  // deepest prefix of levels that is worth sharding (never the coarsest level)
+  int ns = 0;
+  while (ns + 1 < P.n_levels && level_sizes[ns] / world >= min_rows_per_rank) ++ns;
+  // shrink until every block comfortably contains its halos
+  for (; ns > 0; --ns) {
+    bool ok = true;
+    int ghost = 0;
+    for (int l = ns - 1; l >= 0 && ok; --l) {
+      ghost = 2 * ghost + 1;
+      const int64_t need = 4ll * (half_bandwidth[l] + ghost) + (1ll << ns);
+      if (level_sizes[l] / world < need) ok = false;
+    }
+    if (ok) break;
+  }
+  P.n_sharded = ns;
+  if (ns == 0) return P;
+  P.start.assign(ns, std::vector<int64_t>(world + 1, 0));
+  P.halo_lo.assign(ns, 0);
+  P.halo_hi.assign(ns, 0);
+  P.ghost.assign(ns, 0);
+  const int64_t align = 1ll << ns;
+  for (int g = 0; g <= world; ++g) {
+    int64_t s0 = (g == world) ? level_sizes[0] : (level_sizes[0] * g / world) / align * align;
+    for (int l = 0; l < ns; ++l) {
+      P.start[l][g] = (g == world) ? level_sizes[l] : (s0 >> l);
+    }
+  }
+  int ghost = 0;
+  for (int l = ns - 1; l >= 0; --l) {
+    ghost = 2 * ghost + 1;
+    P.ghost[l] = ghost;
+    P.halo_lo[l] = half_bandwidth[l];
+    P.halo_hi[l] = half_bandwidth[l] + ghost;
+  }
+  return P;
+}
+
 // ------------------------------------------------------------------ GS schedule
 
 Schedule gs_schedule(const Csc& M, bool forward) {

@@ -89,6 +89,30 @@ struct Dia {
 };
 constexpr int kMaxDiag = 16;
 Dia build_dia(const Csc& M, const std::vector<int>* rows = nullptr);
+// Rows [row_begin, row_begin + n_rows) of M with local numbering: entry d of
+// local row t multiplies x_local[t + off[d] + x_shift], x_local being this
+// rank's halo-extended vector (x_shift = number of halo elements below).
+Dia build_dia_block(const Csc& M, int row_begin, int n_rows);
+
+// ---- row-block partition of the fine levels over the ranks of one node ----
+// Level l < n_sharded is split into contiguous row blocks [start[l][g], start[l][g+1]);
+// block starts at level 0 are multiples of 2^n_sharded so that the coarse block of
+// a rank is exactly the image of its fine block (coarse row J belongs to the owner of
+// fine row 2J+1).  halo_lo / halo_hi are the u-halo widths a rank keeps below / above
+// its block (half-bandwidth w_l, plus `ghost` on the upper side); `ghost` is the number
+// of extra rows [end, end+ghost) whose residual the rank forms itself so that the fused
+// residual+restriction needs no second exchange: ghost_l = 2*ghost_{l+1} + 1.
+struct PartitionPlan {
+  int world = 1;
+  int n_levels = 0;
+  int n_sharded = 0;                        // levels [0, n_sharded) are sharded
+  std::vector<int64_t> n;                   // level sizes
+  std::vector<std::vector<int64_t>> start;  // [level][rank 0..world]
+  std::vector<int> halo_lo, halo_hi, ghost; // per sharded level
+};
+PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
+                                  const std::vector<int>& half_bandwidth, int world,
+                                  int64_t min_rows_per_rank);
 
 // ---- Gauss-Seidel wavefront schedule on the pruned dependency DAG ----
 // forward: row k depends on rows j<k with M(j,k) != 0 (column k of M used as

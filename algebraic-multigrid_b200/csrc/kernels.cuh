@@ -32,8 +32,9 @@ struct SellView {
 constexpr int kMaxDiagDev = 16;
 struct DiaView {
   int n_rows;   // rows covered by this view
-  int n_cols;   // length of x
-  int ld;       // leading dimension of val (n_rows rounded up to 32)
+  int c_min;    // x may be indexed in [c_min, c_max] relative to the pointer the kernel
+  int c_max;    //   gets (full operator: [0, n-1]; row block: [-halo_lo, n_own+halo_hi-1])
+  int ld;       // leading dimension of val (rows rounded up to 32)
   int n_diag;
   int off[kMaxDiagDev];  // ascending column offsets
   const double* val;     // val[d*ld + t], 0.0 = no entry
@@ -51,12 +52,11 @@ struct DiaViewT : DiaView {};
 template <int ND, class Fn>
 __device__ __forceinline__ void for_each_entry(const DiaViewT<ND>& S, int t, int row, const double* x, Fn&& fn) {
   const double* vp = S.val + t;
-  const int last = S.n_cols - 1;
   double v[ND], xv[ND];
 #pragma unroll
   for (int d = 0; d < ND; ++d) v[d] = (d < S.n_diag) ? vp[(size_t)d * S.ld] : 0.0;
 #pragma unroll
-  for (int d = 0; d < ND; ++d) xv[d] = (d < S.n_diag) ? x[min(max(row + S.off[d], 0), last)] : 0.0;
+  for (int d = 0; d < ND; ++d) xv[d] = (d < S.n_diag) ? x[min(max(row + S.off[d], S.c_min), S.c_max)] : 0.0;
 #pragma unroll
   for (int d = 0; d < ND; ++d)
     if (v[d] != 0.0) fn(row + S.off[d], v[d], xv[d]);
@@ -244,23 +244,25 @@ __global__ void __launch_bounds__(256) k_restrict(const double* __restrict__ r, 
 // u[i] = u[i] + (P e)[i]; (P e)[2J+1] = 0 + 1 e[J]; (P e)[2J] = (0 + .5 e[J-1]) + .5 e[J]
 // with the terms whose coarse index is outside [0, n_coarse) absent
 // (interpolator.hpp:52-56,118-125; multigrid.hpp:294-296).
-__device__ __forceinline__ double prolong_at(const double* __restrict__ e, int n_coarse, int i) {
+// i: global fine row; e[J - e_first] holds coarse entry J (e_first = global index of e[0],
+// non-zero when the coarse vector is a halo-extended row block).
+__device__ __forceinline__ double prolong_at(const double* __restrict__ e, int e_first, int n_coarse, int i) {
   double acc = 0.0;
+  const int J = i >> 1;
   if (i & 1) {
-    const int J = i >> 1;
-    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(1.0, e[J]));
+    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(1.0, e[J - e_first]));
   } else {
-    const int J = i >> 1;
-    if (J - 1 >= 0 && J - 1 < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - 1]));
-    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J]));
+    if (J - 1 >= 0 && J - 1 < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - 1 - e_first]));
+    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - e_first]));
   }
   return acc;
 }
-__global__ void __launch_bounds__(256) k_prolong_add(const double* __restrict__ e, int n_coarse,
-                                                     double* __restrict__ u, int n_fine) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_fine) return;
-  u[i] = __dadd_rn(u[i], prolong_at(e, n_coarse, i));
+// u points at this rank's first owned fine row (global row fine_first), n_own rows.
+__global__ void __launch_bounds__(256) k_prolong_add(const double* __restrict__ e, int e_first, int n_coarse,
+                                                     double* __restrict__ u, int fine_first, int n_own) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_own) return;
+  u[t] = __dadd_rn(u[t], prolong_at(e, e_first, n_coarse, fine_first + t));
 }
 
 // ------------------------------------------------------------------ rss = sum (b - A u)^2

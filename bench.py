@@ -38,6 +38,8 @@ def parse_args():
     p.add_argument("--levels", type=int, default=0, help="0 = coarsen until <= 600 DOF")
     p.add_argument("--smoother", default="jacobi", choices=["jacobi", "color", "gs"])
     p.add_argument("--eps", type=float, default=1.0, help="anisotropy of the +-n coupling")
+    p.add_argument("--min-rows-per-rank", type=int, default=1 << 17,
+                   help="levels with fewer rows per rank are agglomerated (replicated) instead of sharded")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -174,9 +176,18 @@ def run_b200(a):
     torch.cuda.set_device(local)
     amg.lib().amgb_set_device(local)
     dist = None
+    comm = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+        def exchange_id(raw):
+            box = [raw]
+            dist.broadcast_object_list(box, src=0, device=torch.device("cuda", local))
+            return box[0]
+        comm = amg.Comm(rank, world, exchange_id)
+        if a.smoother != "jacobi":
+            raise SystemExit("the sharded V-cycle uses damped Jacobi (Gauss-Seidel is single-GPU)")
 
     levels = a.levels or default_levels(a.n)
     smoother = {"jacobi": amg.DampedJacobi(2.0 / 3.0, 2), "color": amg.MulticolorGaussSeidel(1),
@@ -184,7 +195,8 @@ def run_b200(a):
     t0 = time.perf_counter()
     A = amg.Grid.laplacian(a.n, a.eps)
     b = amg.Grid.rhs(a.n)
-    mg = amg.Multigrid(None, smoother, A, b, levels, 1e-9, 1, 1)
+    mg = amg.Multigrid(None, smoother, A, b, levels, 1e-9, 1, 1, comm=comm,
+                       min_rows_per_rank=a.min_rows_per_rank)
     setup_s = time.perf_counter() - t0
     N0 = mg.get_n_dofs(0)
 
@@ -215,8 +227,8 @@ def run_b200(a):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    # every rank runs the whole problem for now (replicas): whole-job units = world * steps
-    vps = world * a.steps / (ms * 1e-3)
+    # one problem, row blocks spread over the ranks: whole-job V-cycles = steps
+    vps = a.steps / (ms * 1e-3)
     rss_after = mg.rss()
 
     # ---- e2e: host-resident b and u; H2D(b,u) + V-cycle + D2H(u) each step ----
@@ -240,7 +252,7 @@ def run_b200(a):
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * steps_e / dt, "unit": "V-cycles/s",
+        e2e = {"value": steps_e / dt, "unit": "V-cycles/s",
                "h2d_bytes_per_step": 16 * N0, "d2h_bytes_per_step": 8 * N0, "steps": steps_e}
 
     # ---- dominant kernel roofline: the level-0 smoother pass, timed live with CUDA events ----
@@ -251,7 +263,8 @@ def run_b200(a):
     peak, peak_src = measured_hbm_peak()
     kern_ms = mg.time_kernel(0, 0, warmup=3, reps=20)
     n1 = mg.get_n_dofs(1)
-    bytes0 = mg.matrix_bytes(0) + 24 * N0
+    r0, r1 = mg.local_range(0)
+    bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0)       # this rank's row block
     survey0 = mg.pass_bytes(0)
     achieved = bytes0 / (kern_ms * 1e-3) / 1e9
     kname = {"jacobi": "k_jacobi", "color": "k_color_gs", "gs": "k_gs_fronts"}[a.smoother]
@@ -263,7 +276,7 @@ def run_b200(a):
                 "survey_formula_GBps": survey0 / (kern_ms * 1e-3) / 1e9,
                 "traffic": ncu_traffic(kname)}
     per_kernel = {}
-    for kind, nm in ((1, "residual"), (2, "residual_restrict"), (3, "prolong_add")):
+    for kind, nm in ((1, "residual"), (2, "residual_restrict"), (3, "prolong_add")) if world == 1 else ():
         t_ms = mg.time_kernel(0, kind, warmup=3, reps=20)
         alg = {1: bytes0, 2: mg.matrix_bytes(0) + 16 * N0 + 8 * n1, 3: 8 * n1 + 16 * N0}[kind]
         per_kernel[nm] = {"ms": t_ms, "GB/s": alg / (t_ms * 1e-3) / 1e9,
@@ -295,18 +308,21 @@ def run_b200(a):
     out = {
         "metric": "vcycles_per_s", "value": vps, "unit": "V-cycles/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-        "higher_is_better": True, "scaling": "weak" if world > 1 else "strong",
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "n": a.n, "n_dofs": N0, "levels": levels,
                    "smoother": a.smoother, "smoother_iters": smoother.n_iters,
                    "omega": getattr(smoother, "omega", None),
                    "l2_policy": "inputs larger than L2 (level-0 operator+vectors stream %.2f GB per "
                                 "pass, L2 is 126 MB)" % (bytes0 / 1e9),
-                   "parallelism": "single GPU" if world == 1 else "replicas x%d" % world,
+                   "parallelism": "single GPU" if world == 1 else
+                                  "row blocks x%d, %d sharded levels, NCCL halo send/recv (%d exchanges per "
+                                  "V-cycle), coarser levels replicated after one gather" % (
+                                      world, mg.n_sharded_levels(), mg.halo_exchanges_per_vcycle()),
                    "mdof_per_s": vps * N0 / 1e6, "setup_s": setup_s,
                    "rss_after_timed_cycles": rss_after,
                    "vcycle_layout_bytes": layout_bytes,
-                   "vcycle_hbm_frac": layout_bytes / (ms / a.steps * 1e-3) / 1e9 / peak,
+                   "vcycle_hbm_frac": (layout_bytes / (ms / a.steps * 1e-3) / 1e9 / peak) if world == 1 else None,
                    "vcycle_survey_formula_bytes": vbytes,
                    "layouts": [mg.format(l) for l in range(levels)],
                    "kernels_level0": per_kernel},

@@ -144,6 +144,38 @@ int amgb_hierarchy_create(int n_rows, int n_cols, const int* colptr, const int* 
                           const amgb_options* opt, amgb_hierarchy** out);
 int amgb_hierarchy_destroy(amgb_hierarchy* h);
 
+/* ------------------------------------------------------------------------
+ * Row-block sharded hierarchy over the GPUs of one NVSwitch node: one process per
+ * GPU, one communicator per process (no reference counterpart -- the reference is
+ * single-process).  Rank 0 creates the 128-byte id and hands
+ * it to the other ranks by any means (bench.py: torch.distributed broadcast).
+ * Levels with at least min_rows_per_rank rows per rank are split into contiguous row
+ * blocks with NCCL send/recv halo exchange with ranks +-1 before every Jacobi sweep /
+ * residual / prolongation; coarser levels are agglomerated: their right-hand side is
+ * gathered once per cycle and every rank keeps a replica (instead of GPU 0 solving
+ * and scattering back, which would add a second collective).  Every rank passes the
+ * same full A and b; vectors are given / returned at full length.  Damped Jacobi only
+ * (lexicographic Gauss-Seidel is a single-GPU path).
+ * ---------------------------------------------------------------------- */
+typedef struct amgb_comm amgb_comm;
+int amgb_comm_unique_id_bytes(void);
+int amgb_comm_get_unique_id(void* id);
+int amgb_comm_create(const void* id, int rank, int world, amgb_comm** out);
+int amgb_comm_destroy(amgb_comm* comm);
+int amgb_hierarchy_create_sharded(amgb_comm* comm, int64_t min_rows_per_rank, int n_rows, int n_cols,
+                                  const int* colptr, const int* rowidx, const double* val,
+                                  const double* b, int64_t b_rows, const amgb_options* opt,
+                                  amgb_hierarchy** out);
+int amgb_hierarchy_n_sharded_levels(const amgb_hierarchy* h);
+/* rows [begin, end) of `level` this rank owns (the whole level when it is not sharded) */
+int amgb_hierarchy_local_range(const amgb_hierarchy* h, int level, int64_t* begin, int64_t* end);
+int64_t amgb_hierarchy_halo_exchanges_per_vcycle(const amgb_hierarchy* h);
+/* host only: the plan a sharded hierarchy uses.  starts has n_levels*(world+1) slots
+ * (row l holds the world+1 block boundaries of level l), the other arrays n_levels. */
+int amgb_partition_plan(int n_levels, const int64_t* level_sizes, const int* half_bandwidth,
+                        int world, int64_t min_rows_per_rank, int* n_sharded, int64_t* starts,
+                        int* halo_lo, int* halo_hi, int* ghost);
+
 /* make the handle launch on a caller-owned cudaStream_t (NULL = its own stream) */
 int amgb_hierarchy_set_stream(amgb_hierarchy* h, void* cuda_stream);
 

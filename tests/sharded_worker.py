@@ -1,0 +1,74 @@
+"""Worker for the multi-GPU parity test (launched with torch.distributed.run, one rank per
+GPU).  Each rank builds the row-block sharded hierarchy, runs V-cycles and compares the
+gathered iterates with (a) the same hierarchy on one GPU -- damped Jacobi is independent of
+the partition, so the bits must be identical -- and (b) the CPU oracle."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle as O  # noqa: E402
+
+amg = importlib.import_module("algebraic-multigrid_b200")
+
+
+def id_exchanger(rank):
+    def ex(raw):
+        box = [raw]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return ex
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    amg.lib().amgb_set_device(local)
+    dist.init_process_group("gloo")
+    comm = amg.Comm(rank, world, id_exchanger(rank))
+    cases = [(257, 10, 1.0, 1 << 10), (513, 12, 1e-3, 1 << 12)]
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        cases = [(2049, 15, 1.0, 1 << 16)]
+    for n, L, eps, min_rows in cases:
+        A, b = amg.Grid.laplacian(n, eps), amg.Grid.rhs(n)
+        sm = amg.DampedJacobi(2.0 / 3.0, 2)
+        for use_graph in (False, True):
+            mg = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1, comm=comm, min_rows_per_rank=min_rows,
+                               use_graph=use_graph)
+            ns = mg.n_sharded_levels()
+            assert ns >= 2, ns
+            single = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1)
+            for _ in range(3):
+                mg.vcycle()
+                single.vcycle()
+            for l in range(L):
+                got, want = mg.get_soln(l), single.get_soln(l)
+                assert got.tobytes() == want.tobytes(), (n, l, use_graph, np.abs(got - want).max())
+            r_sh, r_one = mg.rss(), single.rss()
+            assert abs(r_sh - r_one) <= 1e-13 * r_one, (r_sh, r_one)
+            if rank == 0 and n <= 600 and not use_graph:
+                mo = O.Multigrid(O.laplacian(n, eps), b, L, 1e-9, 1, 1, O.SMOOTHER_JACOBI, 2, 2.0 / 3.0)
+                for _ in range(3):
+                    mo.vcycle()
+                assert np.linalg.norm(mg.get_soln(0) - mo.u(0)) <= 1e-12 * np.linalg.norm(mo.u(0))
+            else:
+                mg.get_soln(0)  # collective: every rank takes part
+            if rank == 0:
+                print("ok n=%d levels=%d sharded_levels=%d graph=%s halo_exchanges/vcycle=%d rss=%.6e" % (
+                    n, L, ns, use_graph, mg.halo_exchanges_per_vcycle(), r_sh), flush=True)
+            del mg, single
+    dist.barrier()
+    del comm
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SHARDED PARITY OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
