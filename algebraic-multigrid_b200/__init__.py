@@ -58,6 +58,8 @@ SIGNATURES = {
     "amgb_n_H_dofs_from_n_h_dofs": (_l, [_l]),
     "amgb_interp_nnz": (_l, [_l, _l]),
     "amgb_interp_make_operators": (_i, [_l, _l, _pi, _pi, _pd, _pi, _pi, _pd]),
+    "amgb_linear_restrict": (_i, [_l, _l, _pd, _pd]),
+    "amgb_linear_prolong": (_i, [_l, _l, _pd, _pd]),
     "amgb_matrix_create": (_i, [_i, _i, _pi, _pi, _pd, C.POINTER(_p)]),
     "amgb_matrix_destroy": (_i, [_p]),
     "amgb_matrix_nnz_device": (_l, [_p]),

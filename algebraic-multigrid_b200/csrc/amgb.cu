@@ -729,6 +729,33 @@ int amgb_interp_make_operators(int64_t n_h, int64_t n_H, int* P_colptr, int* P_r
   });
 }
 
+int amgb_linear_restrict(int64_t n_h, int64_t n_H, const double* r, double* out) {
+  return guarded([&] {
+    if (!r || !out || n_h < 0 || n_H < 0) throw std::invalid_argument("bad transfer arguments");
+    require_device();
+    DevBuf<double> dr, dout;
+    dr.upload(r, n_h, nullptr);
+    dout.alloc(n_H);
+    if (n_H) LAUNCH(dev::k_restrict, blocks_for(n_H, 256), 256, 0, nullptr, dr.p, (int)n_h, dout.p, (int)n_H);
+    dout.download(out, nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(nullptr));
+  });
+}
+int amgb_linear_prolong(int64_t n_h, int64_t n_H, const double* e, double* out) {
+  return guarded([&] {
+    if (!e || !out || n_h < 0 || n_H < 0) throw std::invalid_argument("bad transfer arguments");
+    require_device();
+    DevBuf<double> de, dout;
+    de.upload(e, n_H, nullptr);
+    dout.alloc(n_h);
+    dout.zero(nullptr);
+    if (n_h)
+      LAUNCH(dev::k_prolong_add, blocks_for(n_h, 256), 256, 0, nullptr, de.p, 0, (int)n_H, dout.p, 0, (int)n_h);
+    dout.download(out, nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(nullptr));
+  });
+}
+
 // ---- amgb_matrix ----
 int amgb_matrix_create(int n_rows, int n_cols, const int* colptr, const int* rowidx, const double* val,
                        amgb_matrix** out) {

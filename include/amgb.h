@@ -87,6 +87,11 @@ int amgb_interp_make_operators(int64_t n_h, int64_t n_H,
                                int* P_colptr, int* P_rowidx, double* P_val,
                                int* R_colptr, int* R_rowidx, double* R_val);
 
+/* Matrix-free grid transfers of LinearInterpolator on host vectors:
+ * out = R r (interpolator.hpp:64-68) and out = P e (interpolator.hpp:52-56). */
+int amgb_linear_restrict(int64_t n_h, int64_t n_H, const double* r, double* out);
+int amgb_linear_prolong(int64_t n_h, int64_t n_H, const double* e, double* out);
+
 /* ------------------------------------------------------------------------
  * Matrix mirror + stand-alone operators (the SmootherBase::smooth boundary,
  * include/amg/smoother.hpp:63-65).  u is updated in place.
