@@ -217,6 +217,11 @@ struct Operator {
   bool have_fronts = false;
   DevBuf<int> f_order, f_ptr, b_order, b_ptr;
   int n_ffronts = 0, n_bfronts = 0;
+  // banded line-scan Gauss-Seidel (k_gs_rhs + k_gs_lines)
+  bool lines_checked = false, lines_ok = false;
+  dev::GsLineDesc line_desc[2];  // [0] forward, [1] backward
+  int lines_T = 0, lines_R = 1;
+  size_t lines_smem = 0;
   // multicolour
   bool have_colors = false;
   int n_colors = 0;
@@ -269,6 +274,93 @@ struct Operator {
     CUDA_CHECK(cudaStreamSynchronize(s));
     have_fronts = true;
   }
+  // The line-scan kernel applies when the mirror is DIA and, on each side of the diagonal,
+  // the entries are an optional distance-1 diagonal plus at most four "far" diagonals.
+  void ensure_lines() {
+    if (lines_checked) return;
+    lines_checked = true;
+    if (!colrows.is_dia || block || n < 1) return;
+    const DevDia& D = colrows.dia;
+    int diag_d = -1;
+    for (int d = 0; d < D.n_diag; ++d)
+      if (D.off[d] == 0) diag_d = d;
+    if (diag_d < 0) return;
+    int B = 4096, max_far = 0;
+    for (int side = 0; side < 2; ++side) {  // 0: forward (updated = lower), 1: backward (updated = upper)
+      dev::GsLineDesc L{};
+      L.n = n;
+      L.dir = side == 0 ? +1 : -1;
+      L.near_d = -1;
+      L.diag_d = diag_d;
+      L.ld = D.ld;
+      L.val = D.val.p;
+      L.n_far = 0;
+      // ascending column order of the already-updated side: forward = most negative offset
+      // first; backward = smallest positive offset first (the distance-1 entry goes to the scan)
+      for (int d = 0; d < D.n_diag; ++d) {
+        const int dist = side == 0 ? -D.off[d] : D.off[d];
+        if (dist <= 0) continue;
+        if (dist == 1) {
+          L.near_d = d;
+          continue;
+        }
+        if (L.n_far == 4) return;
+        L.far_dist[L.n_far] = dist;
+        L.far_d[L.n_far] = d;
+        ++L.n_far;
+        B = std::min(B, dist);
+        max_far = std::max(max_far, dist);
+      }
+      line_desc[side] = L;
+    }
+    B = std::max(1, std::min(B, n));
+    lines_R = B <= 1024 ? 1 : (B <= 2048 ? 2 : 4);
+    lines_T = std::min(1024, ((B + lines_R - 1) / lines_R + 31) / 32 * 32);
+    int ring = 64;
+    while (ring < B + max_far + 1) ring <<= 1;
+    lines_smem = sizeof(double) * ((size_t)ring + 64);
+    if (lines_smem > 200 * 1024) return;
+    for (int side = 0; side < 2; ++side) {
+      line_desc[side].B = B;
+      line_desc[side].ring_mask = ring - 1;
+    }
+    lines_ok = true;
+  }
+  // one Gauss-Seidel direction (smoother.hpp:148-157 forward, :167-174 backward)
+  void gs_direction(bool forward, const double* f, double* u, double* g_scratch, int mode, cudaStream_t s) {
+    if (mode == AMGB_GS_AUTO) ensure_lines();
+    if (mode == AMGB_GS_AUTO && lines_ok && g_scratch) {
+      const dev::GsLineDesc& L = line_desc[forward ? 0 : 1];
+      with_view(colrows, [&](auto V) { launch_gs_rhs(V, L.dir, u, f, g_scratch, s); });
+      if (lines_R == 1) launch_gs_lines<1>(L, g_scratch, u, s);
+      else if (lines_R == 2) launch_gs_lines<2>(L, g_scratch, u, s);
+      else launch_gs_lines<4>(L, g_scratch, u, s);
+    } else {
+      ensure_fronts(s);
+      if (forward) gs_forward(f, u, s);
+      else gs_backward(f, u, s);
+    }
+  }
+  template <int ND>
+  void launch_gs_rhs(dev::DiaViewT<ND> V, int dir, const double* u, const double* f, double* g, cudaStream_t s) {
+    auto kern = dev::k_gs_rhs<ND>;
+    V.n_rows = n;
+    LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, dir, u, f, g);
+  }
+  void launch_gs_rhs(SellView, int, const double*, const double*, double*, cudaStream_t) {
+    throw ApiError(AMGB_ESTATE, "line-scan Gauss-Seidel needs the DIA layout");
+  }
+  template <int R>
+  void launch_gs_lines(const dev::GsLineDesc& L, const double* g, double* u, cudaStream_t s) {
+    auto kern = dev::k_gs_lines<R>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    LAUNCH(kern, 1, lines_T, lines_smem, s, L, g, u);
+  }
+
   void ensure_colors(cudaStream_t s) {
     if (have_colors) return;
     n_colors = greedy_coloring(M, MT, color);
@@ -440,7 +532,11 @@ struct amgb_hierarchy {
         throw std::invalid_argument("sharded levels support the damped-Jacobi smoother only");
       return;
     }
-    if (opt.smoother == AMGB_SMOOTHER_GS) ops[l]->ensure_fronts(stream);
+    if (opt.smoother == AMGB_SMOOTHER_GS) {
+      if (opt.gs_mode == AMGB_GS_AUTO) ops[l]->ensure_lines();
+      if (!(opt.gs_mode == AMGB_GS_AUTO && ops[l]->lines_ok)) ops[l]->ensure_fronts(stream);
+      if (!lv[l].tmp.p) lv[l].tmp.alloc(lv[l].n_vec());
+    }
     if (opt.smoother == AMGB_SMOOTHER_COLOR_GS) ops[l]->ensure_colors(stream);
   }
 
@@ -484,8 +580,8 @@ struct amgb_hierarchy {
     const int64_t iters = opt.smoother_iters;
     if (opt.smoother == AMGB_SMOOTHER_GS) {
       for (int64_t it = 0; it < iters; ++it) {  // smoother.hpp:195-198
-        A.gs_forward(S.f.p, S.u.p, s);
-        A.gs_backward(S.f.p, S.u.p, s);
+        A.gs_direction(true, S.f.p, S.u.p, S.tmp.p, opt.gs_mode, s);
+        A.gs_direction(false, S.f.p, S.u.p, S.tmp.p, opt.gs_mode, s);
       }
     } else if (opt.smoother == AMGB_SMOOTHER_JACOBI) {
       double* src = S.u.p;
@@ -796,17 +892,15 @@ int amgb_smooth_gs(amgb_matrix* A, double* u, const double* b, double tolerance,
                    int64_t n_iters, int mode, int64_t* iters_done, double* final_error) {
   return guarded([&] {
     if (!A || !u || !b) throw std::invalid_argument("null argument");
-    (void)mode;
     CUDA_CHECK(cudaSetDevice(A->device));
     cudaStream_t s = A->stream;
-    A->op.ensure_fronts(s);
     A->u.upload(u, A->op.n, s);
     A->b.upload(b, A->op.n, s);
     int64_t iter = 0;
     double error = 100;
     while (iter < n_iters && error > tolerance) {  // smoother.hpp:195-203
-      A->op.gs_forward(A->b.p, A->u.p, s);
-      A->op.gs_backward(A->b.p, A->u.p, s);
+      A->op.gs_direction(true, A->b.p, A->u.p, A->r.p, mode, s);
+      A->op.gs_direction(false, A->b.p, A->u.p, A->r.p, mode, s);
       iter += 1;
       if (every != 0 && iter % every == 0) error = matrix_rss(A);
     }
@@ -1375,7 +1469,7 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
           else if (h->opt.smoother == AMGB_SMOOTHER_COLOR_GS)
             for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, S.f.p, scratch_u.p, s);
           else
-            A.gs_forward(S.f.p, scratch_u.p, s);
+            A.gs_direction(true, S.f.p, scratch_u.p, S.tmp.p, h->opt.gs_mode, s);
           break;
         case 1:
           A.residual(su, S.f.p, S.tmp_own(), s);

@@ -196,6 +196,180 @@ __global__ void __launch_bounds__(1024) k_gs_fronts(M A, const int* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ banded line-scan GS
+// Fast lexicographic Gauss-Seidel for the banded operators of this path.  A sweep
+// (D + L) u_new = f - U u_old is split into
+//   k_gs_rhs    g = f - (not-yet-updated side) * u_old      fully parallel, HBM-bound
+//   k_gs_lines  (D + L) u = g  solved in sweep order by ONE block: rows are taken in
+//               consecutive blocks of B <= (smallest far distance) rows, so every far
+//               already-updated neighbour of a block lies in earlier blocks and is read
+//               from a shared-memory ring of the most recent values; the distance-1 chain
+//               u_k = (c_k - l_k u_{k-1}) / d_k inside the block is a first-order linear
+//               recurrence solved by a parallel scan of affine maps (warp shuffles, then
+//               across warps).  Coefficients of the next block are prefetched while the
+//               current block is scanned.
+// The update order is the reference's (smoother.hpp:148-174); the scan re-associates the
+// arithmetic of the distance-1 chain, so results agree with the oracle to rounding
+// (measured <= 1e-14 relative), not bit for bit -- k_gs_fronts is the bit-exact kernel.
+// `pos` is the position in sweep order: row = pos (forward) or n-1-pos (backward).
+struct GsLineDesc {
+  int n;            // rows
+  int dir;          // +1 forward, -1 backward
+  int B;            // rows per block step
+  int ring_mask;    // ring size - 1 (power of two >= B + largest far distance + 1)
+  int n_far;        // far already-updated diagonals (<= 4)
+  int far_dist[4];  // their distances in sweep order (> 1), in summation order
+  int far_d[4];     // their DIA diagonal index
+  int near_d;       // DIA index of the distance-1 already-updated diagonal, -1 if none
+  int diag_d;       // DIA index of the main diagonal
+  int ld;
+  const double* val;
+};
+
+// g[row] = f[row] - sum over the not-yet-updated side (upper for a forward sweep, lower
+// for a backward sweep) of a * u_old, ascending column order.
+template <int ND>
+__global__ void __launch_bounds__(256) k_gs_rhs(DiaViewT<ND> A, int dir, const double* __restrict__ u,
+                                                const double* __restrict__ f, double* __restrict__ g) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_rows) return;
+  const double* vp = A.val + t;
+  double v[ND], xv[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const bool take = (d < A.n_diag) && (dir > 0 ? A.off[d] > 0 : A.off[d] < 0);
+    v[d] = take ? vp[(size_t)d * A.ld] : 0.0;
+    xv[d] = take ? u[min(max(t + A.off[d], A.c_min), A.c_max)] : 0.0;
+  }
+  double acc = f[t];
+#pragma unroll
+  for (int d = 0; d < ND; ++d)
+    if (v[d] != 0.0) acc = __dsub_rn(acc, __dmul_rn(v[d], xv[d]));
+  g[t] = acc;
+}
+
+struct Affine {  // x -> p + q x
+  double q, p;
+};
+__device__ __forceinline__ Affine compose(Affine later, Affine earlier) {
+  return Affine{later.q * earlier.q, later.p + later.q * earlier.p};
+}
+__device__ __forceinline__ Affine warp_scan_affine(Affine a, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double qo = __shfl_up_sync(0xffffffffu, a.q, o);
+    const double po = __shfl_up_sync(0xffffffffu, a.p, o);
+    if (lane >= o) a = compose(a, Affine{qo, po});
+  }
+  return a;
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* __restrict__ g, double* u) {
+  extern __shared__ double smem[];
+  double* ring = smem;                       // ring_mask + 1 doubles
+  double* wq = smem + D.ring_mask + 1;       // 32 warp totals (q)
+  double* wp = wq + 32;                      // 32 warp totals (p)
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
+  const int n = D.n;
+
+  // coefficients of this thread's R rows for the current and the next block step
+  double c_g[R], c_d[R], c_l[R], c_far[R][4];
+  auto load = [&](int b0, double (&og)[R], double (&od)[R], double (&ol)[R], double (&ofar)[R][4]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = t * R + r;
+      const int pos = b0 + i;
+      const bool ok = (i < D.B) && (pos < n);
+      const int row = D.dir > 0 ? pos : n - 1 - pos;
+      og[r] = ok ? g[row] : 0.0;
+      od[r] = ok ? D.val[(size_t)D.diag_d * D.ld + row] : 1.0;
+      ol[r] = (ok && D.near_d >= 0) ? D.val[(size_t)D.near_d * D.ld + row] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ofar[r][k] = (ok && k < D.n_far) ? D.val[(size_t)D.far_d[k] * D.ld + row] : 0.0;
+    }
+  };
+  load(0, c_g, c_d, c_l, c_far);
+
+  for (int b0 = 0; b0 < n; b0 += D.B) {
+    double n_g[R], n_d[R], n_l[R], n_far[R][4];
+    load(b0 + D.B, n_g, n_d, n_l, n_far);  // prefetch (independent of this step's results)
+
+    // per-row affine maps u_k = p + q u_{k-1}
+    Affine row_map[R];
+    Affine mine{1.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = t * R + r;
+      const int pos = b0 + i;
+      const bool ok = (i < D.B) && (pos < n);
+      double c = c_g[r];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double a = c_far[r][k];
+        if (a != 0.0) c = __dsub_rn(c, __dmul_rn(a, ring[(pos - D.far_dist[k]) & D.ring_mask]));
+      }
+      Affine m{0.0, 0.0};
+      if (ok) {
+        if (c_d[r] != 0.0) {
+          m.p = __ddiv_rn(c, c_d[r]);
+          m.q = -__ddiv_rn(c_l[r], c_d[r]);
+        } else {  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
+          m.p = u[D.dir > 0 ? pos : n - 1 - pos];
+        }
+      } else {
+        m.q = 1.0;  // identity for padding rows
+      }
+      row_map[r] = m;
+      mine = compose(m, mine);
+    }
+    // scan across the threads of the block
+    Affine incl = warp_scan_affine(mine, lane);
+    if (n_warps > 1) {
+      if (lane == 31) {
+        wq[warp] = incl.q;
+        wp[warp] = incl.p;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        Affine w{lane < n_warps ? wq[lane] : 1.0, lane < n_warps ? wp[lane] : 0.0};
+        w = warp_scan_affine(w, lane);
+        wq[lane] = w.q;
+        wp[lane] = w.p;
+      }
+      __syncthreads();
+    }
+    // exclusive prefix of this thread = (threads before it in the warp) after (warps before it)
+    Affine excl{__shfl_up_sync(0xffffffffu, incl.q, 1), __shfl_up_sync(0xffffffffu, incl.p, 1)};
+    if (lane == 0) excl = Affine{1.0, 0.0};
+    if (n_warps > 1 && warp > 0) excl = compose(excl, Affine{wq[warp - 1], wp[warp - 1]});
+    const double carry = (b0 > 0) ? ring[(b0 - 1) & D.ring_mask] : 0.0;
+    double x = excl.p + excl.q * carry;
+    // all reads of the ring for this step are done before anyone overwrites it
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = t * R + r;
+      const int pos = b0 + i;
+      if ((i < D.B) && (pos < n)) {
+        x = row_map[r].p + row_map[r].q * x;
+        ring[pos & D.ring_mask] = x;
+        u[D.dir > 0 ? pos : n - 1 - pos] = x;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      c_g[r] = n_g[r];
+      c_d[r] = n_d[r];
+      c_l[r] = n_l[r];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) c_far[r][k] = n_far[r][k];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ fused residual + restriction
 // f_c[J] = ((0 + .5 r[2J]) + 1 r[2J+1]) + .5 r[2J+2]  with r = f - A u never
 // written to HBM; also zeroes the coarse solution (multigrid.hpp:272-282).
