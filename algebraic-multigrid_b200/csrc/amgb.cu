@@ -220,7 +220,7 @@ struct Operator {
   // banded line-scan Gauss-Seidel (k_gs_rhs + k_gs_lines)
   bool lines_checked = false, lines_ok = false;
   dev::GsLineDesc line_desc[2];  // [0] forward, [1] backward
-  int lines_T = 0, lines_R = 1;
+  int lines_T = 0, lines_R = 0;  // threads; cp.async stages
   size_t lines_smem = 0;
   // multicolour
   bool have_colors = false;
@@ -313,13 +313,22 @@ struct Operator {
       }
       line_desc[side] = L;
     }
-    B = std::max(1, std::min(B, n));
-    lines_R = B <= 1024 ? 1 : (B <= 2048 ? 2 : 4);
-    lines_T = std::min(1024, ((B + lines_R - 1) / lines_R + 31) / 32 * 32);
+    B = std::max(1, std::min(std::min(B, 1024), n));
+    lines_T = (B + 31) / 32 * 32;
     int ring = 64;
     while (ring < B + max_far + 1) ring <<= 1;
-    lines_smem = sizeof(double) * ((size_t)ring + 64);
-    if (lines_smem > 200 * 1024) return;
+    const int n_far = std::max(line_desc[0].n_far, line_desc[1].n_far);
+    const size_t cap = 220 * 1024;
+    lines_R = 0;  // number of cp.async stages
+    for (int stages : {4, 3, 2}) {
+      const size_t bytes = sizeof(double) * ((size_t)ring + 64 + (size_t)stages * (3 + n_far) * B);
+      if (bytes <= cap) {
+        lines_R = stages;
+        lines_smem = bytes;
+        break;
+      }
+    }
+    if (lines_R == 0) return;
     for (int side = 0; side < 2; ++side) {
       line_desc[side].B = B;
       line_desc[side].ring_mask = ring - 1;
@@ -332,8 +341,8 @@ struct Operator {
     if (mode == AMGB_GS_AUTO && lines_ok && g_scratch) {
       const dev::GsLineDesc& L = line_desc[forward ? 0 : 1];
       with_view(colrows, [&](auto V) { launch_gs_rhs(V, L.dir, u, f, g_scratch, s); });
-      if (lines_R == 1) launch_gs_lines<1>(L, g_scratch, u, s);
-      else if (lines_R == 2) launch_gs_lines<2>(L, g_scratch, u, s);
+      if (lines_R == 2) launch_gs_lines<2>(L, g_scratch, u, s);
+      else if (lines_R == 3) launch_gs_lines<3>(L, g_scratch, u, s);
       else launch_gs_lines<4>(L, g_scratch, u, s);
     } else {
       ensure_fronts(s);
@@ -350,12 +359,12 @@ struct Operator {
   void launch_gs_rhs(SellView, int, const double*, const double*, double*, cudaStream_t) {
     throw ApiError(AMGB_ESTATE, "line-scan Gauss-Seidel needs the DIA layout");
   }
-  template <int R>
+  template <int STAGES>
   void launch_gs_lines(const dev::GsLineDesc& L, const double* g, double* u, cudaStream_t s) {
-    auto kern = dev::k_gs_lines<R>;
+    auto kern = dev::k_gs_lines<STAGES>;
     static bool attr_done = false;
     if (!attr_done) {
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       attr_done = true;
     }
     LAUNCH(kern, 1, lines_T, lines_smem, s, L, g, u);

@@ -15,6 +15,7 @@
 //   rss                   include/amg/common.hpp:17-27
 #pragma once
 #include <cstdint>
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
 namespace amgb {
@@ -264,68 +265,67 @@ __device__ __forceinline__ Affine warp_scan_affine(Affine a, int lane) {
   return a;
 }
 
-template <int R>
+// Coefficients (g, diagonal, distance-1 entry, far entries) of the next block steps are
+// staged into shared memory with cp.async (LDGSTS) STAGES-1 steps ahead; every thread copies
+// and later reads only its own row's slots, so the staging needs no barrier.
+template <int STAGES>
 __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* __restrict__ g, double* u) {
   extern __shared__ double smem[];
-  double* ring = smem;                       // ring_mask + 1 doubles
-  double* wq = smem + D.ring_mask + 1;       // 32 warp totals (q)
-  double* wp = wq + 32;                      // 32 warp totals (p)
+  double* ring = smem;                  // ring_mask + 1 doubles: most recent new values by position
+  double* wq = smem + D.ring_mask + 1;  // 32 warp totals (q)
+  double* wp = wq + 32;                 // 32 warp totals (p)
+  double* stage = wp + 32;              // STAGES x (3 + n_far) x B
   const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
-  const int n = D.n;
+  const int n = D.n, B = D.B, n_arr = 3 + D.n_far;
+  const int n_steps = (n + B - 1) / B;
 
-  // coefficients of this thread's R rows for the current and the next block step
-  double c_g[R], c_d[R], c_l[R], c_far[R][4];
-  auto load = [&](int b0, double (&og)[R], double (&od)[R], double (&ol)[R], double (&ofar)[R][4]) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = t * R + r;
-      const int pos = b0 + i;
-      const bool ok = (i < D.B) && (pos < n);
+  auto issue = [&](int step) {
+    const int pos = step * B + t;
+    if (step < n_steps && t < B && pos < n) {
       const int row = D.dir > 0 ? pos : n - 1 - pos;
-      og[r] = ok ? g[row] : 0.0;
-      od[r] = ok ? D.val[(size_t)D.diag_d * D.ld + row] : 1.0;
-      ol[r] = (ok && D.near_d >= 0) ? D.val[(size_t)D.near_d * D.ld + row] : 0.0;
+      double* dst = stage + (size_t)(step % STAGES) * n_arr * B + t;
+      __pipeline_memcpy_async(dst, g + row, 8);
+      __pipeline_memcpy_async(dst + B, D.val + (size_t)D.diag_d * D.ld + row, 8);
+      if (D.near_d >= 0) __pipeline_memcpy_async(dst + 2 * B, D.val + (size_t)D.near_d * D.ld + row, 8);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        ofar[r][k] = (ok && k < D.n_far) ? D.val[(size_t)D.far_d[k] * D.ld + row] : 0.0;
+        if (k < D.n_far) __pipeline_memcpy_async(dst + (3 + k) * B, D.val + (size_t)D.far_d[k] * D.ld + row, 8);
     }
+    __pipeline_commit();
   };
-  load(0, c_g, c_d, c_l, c_far);
+  for (int st = 0; st < STAGES - 1; ++st) issue(st);
 
-  for (int b0 = 0; b0 < n; b0 += D.B) {
-    double n_g[R], n_d[R], n_l[R], n_far[R][4];
-    load(b0 + D.B, n_g, n_d, n_l, n_far);  // prefetch (independent of this step's results)
-
-    // per-row affine maps u_k = p + q u_{k-1}
-    Affine row_map[R];
-    Affine mine{1.0, 0.0};
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = t * R + r;
-      const int pos = b0 + i;
-      const bool ok = (i < D.B) && (pos < n);
-      double c = c_g[r];
+  for (int step = 0; step < n_steps; ++step) {
+    issue(step + STAGES - 1);
+    __pipeline_wait_prior(STAGES - 1);  // this step's slots have landed
+    const int b0 = step * B;
+    const int pos = b0 + t;
+    const bool ok = (t < B) && (pos < n);
+    Affine m{1.0, 0.0};  // identity for padding threads
+    if (ok) {
+      const double* src = stage + (size_t)(step % STAGES) * n_arr * B + t;
+      double c = src[0];
+      const double d = src[B];
+      const double l = D.near_d >= 0 ? src[2 * B] : 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const double a = c_far[r][k];
-        if (a != 0.0) c = __dsub_rn(c, __dmul_rn(a, ring[(pos - D.far_dist[k]) & D.ring_mask]));
-      }
-      Affine m{0.0, 0.0};
-      if (ok) {
-        if (c_d[r] != 0.0) {
-          m.p = __ddiv_rn(c, c_d[r]);
-          m.q = -__ddiv_rn(c_l[r], c_d[r]);
-        } else {  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
-          m.p = u[D.dir > 0 ? pos : n - 1 - pos];
+        if (k < D.n_far) {
+          const double a = src[(3 + k) * B];
+          if (a != 0.0) c = __dsub_rn(c, __dmul_rn(a, ring[(pos - D.far_dist[k]) & D.ring_mask]));
         }
-      } else {
-        m.q = 1.0;  // identity for padding rows
       }
-      row_map[r] = m;
-      mine = compose(m, mine);
+      if (d != 0.0) {
+        m.p = __ddiv_rn(c, d);
+        m.q = -__ddiv_rn(l, d);
+      } else {  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
+        m.p = u[D.dir > 0 ? pos : n - 1 - pos];
+        m.q = 0.0;
+      }
     }
-    // scan across the threads of the block
-    Affine incl = warp_scan_affine(mine, lane);
+    const double carry = (b0 > 0) ? ring[(b0 - 1) & D.ring_mask] : 0.0;
+    // inclusive scan of the affine maps over the block
+    Affine incl = warp_scan_affine(m, lane);
+    Affine before{1.0, 0.0};  // composite of all earlier warps
     if (n_warps > 1) {
       if (lane == 31) {
         wq[warp] = incl.q;
@@ -338,35 +338,18 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
         wq[lane] = w.q;
         wp[lane] = w.p;
       }
-      __syncthreads();
+      __syncthreads();  // also: every ring read of this step happened before this point
+      if (warp > 0) before = Affine{wq[warp - 1], wp[warp - 1]};
+    } else {
+      __syncwarp();
     }
-    // exclusive prefix of this thread = (threads before it in the warp) after (warps before it)
-    Affine excl{__shfl_up_sync(0xffffffffu, incl.q, 1), __shfl_up_sync(0xffffffffu, incl.p, 1)};
-    if (lane == 0) excl = Affine{1.0, 0.0};
-    if (n_warps > 1 && warp > 0) excl = compose(excl, Affine{wq[warp - 1], wp[warp - 1]});
-    const double carry = (b0 > 0) ? ring[(b0 - 1) & D.ring_mask] : 0.0;
-    double x = excl.p + excl.q * carry;
-    // all reads of the ring for this step are done before anyone overwrites it
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = t * R + r;
-      const int pos = b0 + i;
-      if ((i < D.B) && (pos < n)) {
-        x = row_map[r].p + row_map[r].q * x;
-        ring[pos & D.ring_mask] = x;
-        u[D.dir > 0 ? pos : n - 1 - pos] = x;
-      }
+    const Affine total = compose(incl, before);
+    const double x = total.p + total.q * carry;
+    if (ok) {
+      ring[pos & D.ring_mask] = x;
+      u[D.dir > 0 ? pos : n - 1 - pos] = x;
     }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      c_g[r] = n_g[r];
-      c_d[r] = n_d[r];
-      c_l[r] = n_l[r];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) c_far[r][k] = n_far[r][k];
-    }
+    __syncthreads();  // ring complete before the next step gathers from it
   }
 }
 

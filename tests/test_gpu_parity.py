@@ -294,7 +294,13 @@ def test_amg_solve_golden(capsys, mode):
     assert mo.iters_done == 35                                   # identical iteration counts
     hist, hist_o = mg.error_history(), mo.history()
     assert len(hist) == len(hist_o) == 7
-    np.testing.assert_allclose(hist, hist_o, rtol=RTOL)          # residual norms
+    if mode == amg.GS_LEVELSCHED:
+        np.testing.assert_allclose(hist, hist_o, rtol=RTOL)      # residual norms, bit-exact kernels
+    else:
+        # The scan re-associates the distance-1 chain: iterates agree to ~1e-16, but a residual
+        # that has dropped 11 orders of magnitude is a difference of nearly equal numbers, so
+        # its RELATIVE agreement is limited to (1e-16 * |A||u|)^2-level noise over sum r^2.
+        np.testing.assert_allclose(hist, hist_o, rtol=1e-6, atol=RTOL * hist_o[0])
     amg_error = amg.rss(A, amg_u, b)
     assert amg_error < mg.get_tolerance()                        # testlib.cpp:206
     assert "%.6g" % amg_error == "7.19199e-11"                   # README screenshot
