@@ -276,52 +276,41 @@ struct Operator {
   }
   // The line-scan kernel applies when the mirror is DIA and, on each side of the diagonal,
   // the entries are an optional distance-1 diagonal plus at most four "far" diagonals.
-  void ensure_lines() {
+  // Builds, per direction, the sweep-position-ordered static arrays the kernel streams.
+  DevBuf<double> line_coef[2];  // [dinv | q | far_0 .. far_{k-1}], each np entries
+  void ensure_lines(cudaStream_t s) {
     if (lines_checked) return;
     lines_checked = true;
     if (!colrows.is_dia || block || n < 1) return;
     const DevDia& D = colrows.dia;
-    int diag_d = -1;
-    for (int d = 0; d < D.n_diag; ++d)
-      if (D.off[d] == 0) diag_d = d;
-    if (diag_d < 0) return;
-    int B = 4096, max_far = 0;
+    bool has_diag = false;
+    for (int d = 0; d < D.n_diag; ++d) has_diag |= (D.off[d] == 0);
+    if (!has_diag) return;
+    int B = 1024, max_far = 0;
+    std::vector<int> dists[2];
     for (int side = 0; side < 2; ++side) {  // 0: forward (updated = lower), 1: backward (updated = upper)
-      dev::GsLineDesc L{};
-      L.n = n;
-      L.dir = side == 0 ? +1 : -1;
-      L.near_d = -1;
-      L.diag_d = diag_d;
-      L.ld = D.ld;
-      L.val = D.val.p;
-      L.n_far = 0;
       // ascending column order of the already-updated side: forward = most negative offset
       // first; backward = smallest positive offset first (the distance-1 entry goes to the scan)
       for (int d = 0; d < D.n_diag; ++d) {
         const int dist = side == 0 ? -D.off[d] : D.off[d];
-        if (dist <= 0) continue;
-        if (dist == 1) {
-          L.near_d = d;
-          continue;
-        }
-        if (L.n_far == 4) return;
-        L.far_dist[L.n_far] = dist;
-        L.far_d[L.n_far] = d;
-        ++L.n_far;
+        if (dist <= 1) continue;
+        if (dists[side].size() == 4) return;
+        dists[side].push_back(dist);
         B = std::min(B, dist);
         max_far = std::max(max_far, dist);
       }
-      line_desc[side] = L;
     }
-    B = std::max(1, std::min(std::min(B, 1024), n));
+    B = std::min(B, n);
+    B &= ~1;  // even: every step's slice starts on a 16-byte boundary (TMA)
+    if (B < 2) return;
     lines_T = (B + 31) / 32 * 32;
     int ring = 64;
     while (ring < B + max_far + 1) ring <<= 1;
-    const int n_far = std::max(line_desc[0].n_far, line_desc[1].n_far);
+    const int n_far = (int)std::max(dists[0].size(), dists[1].size());
     const size_t cap = 220 * 1024;
-    lines_R = 0;  // number of cp.async stages
+    lines_R = 0;  // number of TMA stages
     for (int stages : {4, 3, 2}) {
-      const size_t bytes = sizeof(double) * ((size_t)ring + 64 + (size_t)stages * (3 + n_far) * B);
+      const size_t bytes = sizeof(double) * ((size_t)ring + 64 + 8 + (size_t)stages * (3 + n_far) * B);
       if (bytes <= cap) {
         lines_R = stages;
         lines_smem = bytes;
@@ -329,15 +318,51 @@ struct Operator {
       }
     }
     if (lines_R == 0) return;
+    const int np = ((n + 1) & ~1) + 2;
     for (int side = 0; side < 2; ++side) {
-      line_desc[side].B = B;
-      line_desc[side].ring_mask = ring - 1;
+      const int nf = (int)dists[side].size();
+      std::vector<double> coef((size_t)(2 + nf) * np, 0.0);
+      double* dinv = coef.data();
+      double* q = dinv + np;
+      double qmax = 0.0;
+      for (int k = 0; k < n; ++k) {
+        const int pos = side == 0 ? k : n - 1 - k;
+        double diag = 0.0, near = 0.0;
+        for (int p = M.colptr[k]; p < M.colptr[k + 1]; ++p) {
+          const double a = M.val[p];
+          if (a == 0.0) continue;
+          const int dist = side == 0 ? k - M.rowidx[p] : M.rowidx[p] - k;
+          if (dist == 0) diag = a;
+          else if (dist == 1) near = a;
+          else if (dist > 1)
+            for (int j = 0; j < nf; ++j)
+              if (dists[side][j] == dist) coef[(size_t)(2 + j) * np + pos] = a;
+        }
+        dinv[pos] = diag != 0.0 ? 1.0 / diag : 0.0;
+        q[pos] = diag != 0.0 ? -(near / diag) : 0.0;
+        qmax = std::max(qmax, std::fabs(q[pos]));
+      }
+      line_coef[side].upload(coef, s);
+      dev::GsLineDesc L{};
+      L.n = n;
+      L.dir = side == 0 ? +1 : -1;
+      L.B = B;
+      L.ring_mask = ring - 1;
+      L.n_far = nf;
+      for (int j = 0; j < nf; ++j) L.far_dist[j] = dists[side][j];
+      L.short_carry = std::pow(qmax, 32.0) < 5.4e-20 ? 1 : 0;
+      L.np = np;
+      L.dinv = line_coef[side].p;
+      L.q = line_coef[side].p + np;
+      L.far = line_coef[side].p + 2 * (size_t)np;
+      line_desc[side] = L;
     }
+    CUDA_CHECK(cudaStreamSynchronize(s));
     lines_ok = true;
   }
   // one Gauss-Seidel direction (smoother.hpp:148-157 forward, :167-174 backward)
   void gs_direction(bool forward, const double* f, double* u, double* g_scratch, int mode, cudaStream_t s) {
-    if (mode == AMGB_GS_AUTO) ensure_lines();
+    if (mode == AMGB_GS_AUTO) ensure_lines(s);
     if (mode == AMGB_GS_AUTO && lines_ok && g_scratch) {
       const dev::GsLineDesc& L = line_desc[forward ? 0 : 1];
       with_view(colrows, [&](auto V) { launch_gs_rhs(V, L.dir, u, f, g_scratch, s); });
@@ -542,9 +567,9 @@ struct amgb_hierarchy {
       return;
     }
     if (opt.smoother == AMGB_SMOOTHER_GS) {
-      if (opt.gs_mode == AMGB_GS_AUTO) ops[l]->ensure_lines();
+      if (opt.gs_mode == AMGB_GS_AUTO) ops[l]->ensure_lines(stream);
       if (!(opt.gs_mode == AMGB_GS_AUTO && ops[l]->lines_ok)) ops[l]->ensure_fronts(stream);
-      if (!lv[l].tmp.p) lv[l].tmp.alloc(lv[l].n_vec());
+      if (!lv[l].tmp.p) lv[l].tmp.alloc(lv[l].n_vec() + 4);
     }
     if (opt.smoother == AMGB_SMOOTHER_COLOR_GS) ops[l]->ensure_colors(stream);
   }
@@ -873,7 +898,7 @@ int amgb_matrix_create(int n_rows, int n_cols, const int* colptr, const int* row
     m->op.build(csc_from_arrays(n_rows, n_cols, colptr, rowidx, val), m->stream);
     m->u.alloc(n_cols);
     m->b.alloc(n_cols);
-    m->r.alloc(n_cols);
+    m->r.alloc((size_t)n_cols + 4);
     m->partial.alloc(m->op.rss_blocks());
     m->scalar.alloc(1);
     *out = m.release();
@@ -969,7 +994,7 @@ int amgb_residual(amgb_matrix* A, const double* u, const double* f, double* r) {
     A->u.upload(u, A->op.n, s);
     A->b.upload(f, A->op.n, s);
     A->op.residual(A->u.p, A->b.p, A->r.p, s);
-    A->r.download(r, s);
+    if (A->op.n) CUDA_CHECK(cudaMemcpyAsync(r, A->r.p, sizeof(double) * A->op.n, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
   });
 }
@@ -1460,7 +1485,7 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
     h->prepare_smoother(level);
     Operator& A = *h->ops[level];
     LevelState& S = h->lv[level];
-    if (!S.tmp.p) S.tmp.alloc(S.n_vec());
+    if (!S.tmp.p) S.tmp.alloc(S.n_vec() + 4);
     DevBuf<double> scratch_u, scratch_c, scratch_c2;
     scratch_u.alloc(S.n_vec());
     CUDA_CHECK(cudaMemcpyAsync(scratch_u.p, S.u.p, sizeof(double) * S.n_vec(), cudaMemcpyDeviceToDevice, s));

@@ -216,15 +216,17 @@ __global__ void __launch_bounds__(1024) k_gs_fronts(M A, const int* __restrict__
 struct GsLineDesc {
   int n;            // rows
   int dir;          // +1 forward, -1 backward
-  int B;            // rows per block step
+  int B;            // rows per block step (even, <= smallest far distance, <= 1024)
   int ring_mask;    // ring size - 1 (power of two >= B + largest far distance + 1)
   int n_far;        // far already-updated diagonals (<= 4)
   int far_dist[4];  // their distances in sweep order (> 1), in summation order
-  int far_d[4];     // their DIA diagonal index
-  int near_d;       // DIA index of the distance-1 already-updated diagonal, -1 if none
-  int diag_d;       // DIA index of the main diagonal
-  int ld;
-  const double* val;
+  int short_carry;  // 1: max|q|^32 is below fp64 resolution, a warp only needs its predecessor
+  int np;           // padded length of the position-ordered arrays (multiple of 2, >= n + 2)
+  // static coefficients in SWEEP-POSITION order (pos = row forward, n-1-row backward), so
+  // one block step reads a contiguous, 16-byte aligned range of each: TMA bulk copies
+  const double* dinv;  // 1 / a_kk (0 where the diagonal is zero or absent)
+  const double* q;     // -(a_{k,prev} / a_kk), the distance-1 chain coefficient
+  const double* far;   // n_far arrays of np entries
 };
 
 // g[row] = f[row] - sum over the not-yet-updated side (upper for a forward sweep, lower
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) k_gs_rhs(DiaViewT<ND> A, int dir, const d
 #pragma unroll
   for (int d = 0; d < ND; ++d)
     if (v[d] != 0.0) acc = __dsub_rn(acc, __dmul_rn(v[d], xv[d]));
-  g[t] = acc;
+  g[dir > 0 ? t : A.n_rows - 1 - t] = acc;  // sweep-position order
 }
 
 struct Affine {  // x -> p + q x
@@ -265,48 +267,86 @@ __device__ __forceinline__ Affine warp_scan_affine(Affine a, int lane) {
   return a;
 }
 
-// Coefficients (g, diagonal, distance-1 entry, far entries) of the next block steps are
-// staged into shared memory with cp.async (LDGSTS) STAGES-1 steps ahead; every thread copies
-// and later reads only its own row's slots, so the staging needs no barrier.
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// One block, rows taken in sweep order in block steps of B.  Per step: the step's slices of
+// g / dinv / q / far coefficients arrive by TMA (issued STAGES-1 steps ahead by thread 0),
+// every thread forms c = g - sum far * u_new (ring), p = c * dinv, scans the affine maps
+// u_k = p_k + q_k u_{k-1}, and publishes u to the ring and to global memory.
 template <int STAGES>
 __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* __restrict__ g, double* u) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   double* ring = smem;                  // ring_mask + 1 doubles: most recent new values by position
   double* wq = smem + D.ring_mask + 1;  // 32 warp totals (q)
   double* wp = wq + 32;                 // 32 warp totals (p)
-  double* stage = wp + 32;              // STAGES x (3 + n_far) x B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wp + 32);  // STAGES mbarriers (8 slots reserved)
+  double* stage = wp + 32 + 8;          // STAGES x (3 + n_far) x B
   const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
   const int n = D.n, B = D.B, n_arr = 3 + D.n_far;
   const int n_steps = (n + B - 1) / B;
 
-  auto issue = [&](int step) {
-    const int pos = step * B + t;
-    if (step < n_steps && t < B && pos < n) {
-      const int row = D.dir > 0 ? pos : n - 1 - pos;
-      double* dst = stage + (size_t)(step % STAGES) * n_arr * B + t;
-      __pipeline_memcpy_async(dst, g + row, 8);
-      __pipeline_memcpy_async(dst + B, D.val + (size_t)D.diag_d * D.ld + row, 8);
-      if (D.near_d >= 0) __pipeline_memcpy_async(dst + 2 * B, D.val + (size_t)D.near_d * D.ld + row, 8);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < D.n_far) __pipeline_memcpy_async(dst + (3 + k) * B, D.val + (size_t)D.far_d[k] * D.ld + row, 8);
-    }
-    __pipeline_commit();
+  if (t == 0) {
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int step) {  // thread 0 only
+    if (step >= n_steps) return;
+    const int b0 = step * B;
+    const int cnt = min(B, n - b0);
+    const uint32_t bytes = (uint32_t)((cnt + 1) & ~1) * 8u;  // arrays are padded, b0 is even
+    const int sidx = step % STAGES;
+    double* dst = stage + (size_t)sidx * n_arr * B;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&bars[sidx], bytes * (uint32_t)n_arr);
+    tma_load_1d(dst, g + b0, bytes, &bars[sidx]);
+    tma_load_1d(dst + B, D.dinv + b0, bytes, &bars[sidx]);
+    tma_load_1d(dst + 2 * B, D.q + b0, bytes, &bars[sidx]);
+    for (int k = 0; k < D.n_far; ++k)
+      tma_load_1d(dst + (3 + k) * B, D.far + (size_t)k * D.np + b0, bytes, &bars[sidx]);
   };
-  for (int st = 0; st < STAGES - 1; ++st) issue(st);
+  if (t == 0)
+    for (int st = 0; st < STAGES - 1; ++st) issue(st);
 
   for (int step = 0; step < n_steps; ++step) {
-    issue(step + STAGES - 1);
-    __pipeline_wait_prior(STAGES - 1);  // this step's slots have landed
+    if (t == 0) issue(step + STAGES - 1);  // its buffer was released by the barrier ending step-1
+    mbar_wait(&bars[step % STAGES], (uint32_t)((step / STAGES) & 1));
     const int b0 = step * B;
     const int pos = b0 + t;
     const bool ok = (t < B) && (pos < n);
     Affine m{1.0, 0.0};  // identity for padding threads
+    bool keep = false;
     if (ok) {
       const double* src = stage + (size_t)(step % STAGES) * n_arr * B + t;
       double c = src[0];
-      const double d = src[B];
-      const double l = D.near_d >= 0 ? src[2 * B] : 0.0;
+      const double dinv = src[B];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (k < D.n_far) {
@@ -314,19 +354,28 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
           if (a != 0.0) c = __dsub_rn(c, __dmul_rn(a, ring[(pos - D.far_dist[k]) & D.ring_mask]));
         }
       }
-      if (d != 0.0) {
-        m.p = __ddiv_rn(c, d);
-        m.q = -__ddiv_rn(l, d);
-      } else {  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
+      m.p = c * dinv;
+      m.q = src[2 * B];
+      keep = (dinv == 0.0);  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
+      if (keep) {
         m.p = u[D.dir > 0 ? pos : n - 1 - pos];
         m.q = 0.0;
       }
     }
     const double carry = (b0 > 0) ? ring[(b0 - 1) & D.ring_mask] : 0.0;
-    // inclusive scan of the affine maps over the block
-    Affine incl = warp_scan_affine(m, lane);
-    Affine before{1.0, 0.0};  // composite of all earlier warps
-    if (n_warps > 1) {
+    const Affine incl = warp_scan_affine(m, lane);
+    double x;
+    if (n_warps == 1) {
+      x = incl.p + incl.q * carry;
+      __syncwarp();
+    } else if (D.short_carry) {
+      // |q|^32 < 2^-64: what enters a warp from further back than its predecessor is below
+      // the last bit, so the value entering warp w is the predecessor's own last value
+      if (lane == 31) wp[warp] = incl.p;
+      __syncthreads();  // also: every ring read of this step happened before this point
+      const double in = (warp == 0) ? carry : wp[warp - 1];
+      x = incl.p + incl.q * in;
+    } else {
       if (lane == 31) {
         wq[warp] = incl.q;
         wp[warp] = incl.p;
@@ -338,18 +387,16 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
         wq[lane] = w.q;
         wp[lane] = w.p;
       }
-      __syncthreads();  // also: every ring read of this step happened before this point
-      if (warp > 0) before = Affine{wq[warp - 1], wp[warp - 1]};
-    } else {
-      __syncwarp();
+      __syncthreads();
+      const Affine before = warp > 0 ? Affine{wq[warp - 1], wp[warp - 1]} : Affine{1.0, 0.0};
+      const Affine total = compose(incl, before);
+      x = total.p + total.q * carry;
     }
-    const Affine total = compose(incl, before);
-    const double x = total.p + total.q * carry;
     if (ok) {
       ring[pos & D.ring_mask] = x;
       u[D.dir > 0 ? pos : n - 1 - pos] = x;
     }
-    __syncthreads();  // ring complete before the next step gathers from it
+    __syncthreads();  // ring complete (and this step's stage buffer free) before the next step
   }
 }
 
