@@ -323,7 +323,7 @@ def test_solve_iteration_counts_match_oracle(name, mk):
 
 def test_solve_resumes_from_stored_solution():
     """solve() continues from level_to_soln[0] (multigrid.hpp:101,336)."""
-    mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel(), every=5, n_iters=10)
+    mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel(mode=amg.GS_LEVELSCHED), every=5, n_iters=10)
     mg.solve(); mo.solve()
     assert mg.iters_done == mo.iters_done == 10
     mg.solve(); mo.solve()
