@@ -350,7 +350,7 @@ struct Operator {
       L.ring_mask = ring - 1;
       L.n_far = nf;
       for (int j = 0; j < nf; ++j) L.far_dist[j] = dists[side][j];
-      L.short_carry = std::pow(qmax, 32.0) < 5.4e-20 ? 1 : 0;
+      L.short_carry = std::pow(qmax, 32.0) <= 0x1p-60 ? 1 : 0;  // below half an ulp of what it is added to
       L.np = np;
       L.dinv = line_coef[side].p;
       L.q = line_coef[side].p + np;

@@ -335,16 +335,18 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
   if (t == 0)
     for (int st = 0; st < STAGES - 1; ++st) issue(st);
 
+  const int stage_stride = n_arr * B;
+  int sidx = 0, phase = 0;
   for (int step = 0; step < n_steps; ++step) {
     if (t == 0) issue(step + STAGES - 1);  // its buffer was released by the barrier ending step-1
-    mbar_wait(&bars[step % STAGES], (uint32_t)((step / STAGES) & 1));
+    mbar_wait(&bars[sidx], (uint32_t)phase);
     const int b0 = step * B;
     const int pos = b0 + t;
     const bool ok = (t < B) && (pos < n);
     Affine m{1.0, 0.0};  // identity for padding threads
     bool keep = false;
     if (ok) {
-      const double* src = stage + (size_t)(step % STAGES) * n_arr * B + t;
+      const double* src = stage + sidx * stage_stride + t;
       double c = src[0];
       const double dinv = src[B];
 #pragma unroll
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
       x = incl.p + incl.q * carry;
       __syncwarp();
     } else if (D.short_carry) {
-      // |q|^32 < 2^-64: what enters a warp from further back than its predecessor is below
+      // |q|^32 <= 2^-60: what enters a warp from further back than its predecessor is below
       // the last bit, so the value entering warp w is the predecessor's own last value
       if (lane == 31) wp[warp] = incl.p;
       __syncthreads();  // also: every ring read of this step happened before this point
@@ -397,6 +399,10 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
       u[D.dir > 0 ? pos : n - 1 - pos] = x;
     }
     __syncthreads();  // ring complete (and this step's stage buffer free) before the next step
+    if (++sidx == STAGES) {
+      sidx = 0;
+      phase ^= 1;
+    }
   }
 }
 
