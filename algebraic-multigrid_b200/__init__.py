@@ -83,6 +83,8 @@ SIGNATURES = {
     "amgb_hierarchy_n_sharded_levels": (_i, [_p]),
     "amgb_hierarchy_local_range": (_i, [_p, _i, C.POINTER(_l), C.POINTER(_l)]),
     "amgb_hierarchy_halo_exchanges_per_vcycle": (_l, [_p]),
+    "amgb_hierarchy_halo_mode": (_i, [_p]),
+    "amgb_hierarchy_halo_timed_out": (_i, [_p]),
     "amgb_partition_plan": (_i, [_i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _pi, _i, _l,
                                  C.POINTER(_i), np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
                                  _pi, _pi, _pi]),
@@ -548,6 +550,12 @@ class Multigrid:
 
     def halo_exchanges_per_vcycle(self):
         return lib().amgb_hierarchy_halo_exchanges_per_vcycle(self.h)
+
+    def halo_mode(self):
+        return {0: "none", 1: "nccl", 2: "peer"}[lib().amgb_hierarchy_halo_mode(self.h)]
+
+    def halo_timed_out(self):
+        return bool(lib().amgb_hierarchy_halo_timed_out(self.h))
 
     # ---- measurement helpers ----
     def set_stream(self, cuda_stream):

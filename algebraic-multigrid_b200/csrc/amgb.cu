@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -551,11 +552,103 @@ struct amgb_hierarchy {
   PartitionPlan plan;
   int n_sharded = 0;
   int64_t halo_exchanges_per_vcycle = 0;
+  // peer-memory halo exchange (CUDA IPC): per sharded level and vector (0 = u, 1 = tmp) the
+  // neighbours' base pointers, plus epoch flags; falls back to NCCL send/recv when unavailable
+  bool p2p = false;
+  struct PeerMap {
+    double* lo[2] = {nullptr, nullptr};  // rank g-1's u / tmp base
+    double* hi[2] = {nullptr, nullptr};  // rank g+1's u / tmp base
+    int lo_halo_lo = 0, lo_n_own = 0;    // geometry of rank g-1's block on this level
+  };
+  std::vector<PeerMap> peers;
+  std::vector<void*> ipc_opened;
+  DevBuf<unsigned long long> flags;      // [site][2]: bumped by the lower / upper neighbour
+  unsigned long long* peer_flags_lo = nullptr;  // rank g-1's flags array
+  unsigned long long* peer_flags_hi = nullptr;  // rank g+1's flags array
+  DevBuf<unsigned long long> epochs;     // [site][2]
+  DevBuf<int> timed_out;
+  int n_sites = 0, site_cursor = 0;
+  static constexpr int kMaxSites = 4096;
 
   ~amgb_hierarchy() {
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     if (own_stream) cudaStreamDestroy(own_stream);
+  }
+  // Map the neighbours' level vectors and flag arrays into this process.
+  void setup_p2p() {
+    if (!comm || world() < 2 || n_sharded == 0) return;
+    const char* env = std::getenv("AMGB_HALO");
+    if (env && std::string(env) == "nccl") return;
+    const int G = world(), g = rank();
+    flags.alloc((size_t)kMaxSites * 2);
+    flags.zero(stream);
+    epochs.alloc((size_t)kMaxSites * 2);
+    epochs.zero(stream);
+    timed_out.alloc(1);
+    timed_out.zero(stream);
+    // handles: per rank [flags, then u and tmp of every sharded level]
+    const int per_rank = 1 + 2 * n_sharded;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);  // 64 bytes = 8 doubles
+    std::vector<cudaIpcMemHandle_t> mine(per_rank);
+    bool ok = cudaIpcGetMemHandle(&mine[0], flags.p) == cudaSuccess;
+    for (int l = 0; l < n_sharded && ok; ++l) {
+      ok = ok && cudaIpcGetMemHandle(&mine[1 + 2 * l], lv[l].u.p) == cudaSuccess;
+      ok = ok && cudaIpcGetMemHandle(&mine[2 + 2 * l], lv[l].tmp.p) == cudaSuccess;
+    }
+    cudaGetLastError();
+    // all-gather (handles, ok flag) through NCCL on a device staging buffer
+    const size_t dbl_per_rank = per_rank * hb / sizeof(double) + 1;
+    DevBuf<double> stage;
+    stage.alloc(dbl_per_rank * G);
+    std::vector<double> host(dbl_per_rank * G, 0.0);
+    std::memcpy(&host[dbl_per_rank * g], mine.data(), per_rank * hb);
+    host[dbl_per_rank * g + dbl_per_rank - 1] = ok ? 1.0 : 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(stage.p + dbl_per_rank * g, &host[dbl_per_rank * g], dbl_per_rank * sizeof(double),
+                               cudaMemcpyHostToDevice, stream));
+    std::vector<int64_t> st(G + 1);
+    for (int r = 0; r <= G; ++r) st[r] = (int64_t)dbl_per_rank * r;
+    allgather_blocks(stage.p, st, stream);
+    CUDA_CHECK(cudaMemcpyAsync(host.data(), stage.p, host.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    bool all_ok = true;
+    for (int r = 0; r < G; ++r) all_ok = all_ok && host[dbl_per_rank * r + dbl_per_rank - 1] == 1.0;
+    if (!all_ok) return;
+    auto open = [&](int r, int idx) -> void* {
+      cudaIpcMemHandle_t hnd;
+      std::memcpy(&hnd, reinterpret_cast<const char*>(&host[dbl_per_rank * r]) + idx * hb, hb);
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      ipc_opened.push_back(p);
+      return p;
+    };
+    peers.assign(n_sharded, PeerMap());
+    bool mapped = true;
+    if (g > 0) mapped = mapped && (peer_flags_lo = (unsigned long long*)open(g - 1, 0));
+    if (g + 1 < G) mapped = mapped && (peer_flags_hi = (unsigned long long*)open(g + 1, 0));
+    for (int l = 0; l < n_sharded && mapped; ++l) {
+      for (int v = 0; v < 2; ++v) {
+        if (g > 0) mapped = mapped && (peers[l].lo[v] = (double*)open(g - 1, 1 + 2 * l + v));
+        if (g + 1 < G) mapped = mapped && (peers[l].hi[v] = (double*)open(g + 1, 1 + 2 * l + v));
+      }
+      if (g > 0) {
+        peers[l].lo_halo_lo = plan.halo_lo[l];
+        peers[l].lo_n_own = (int)(plan.start[l][g] - plan.start[l][g - 1]);
+      }
+    }
+    // every rank must agree, otherwise some would wait for flags nobody bumps
+    scalar_host_and(mapped);
+    p2p = mapped;
+  }
+  // logical AND of a host bool over all ranks (NCCL all-reduce of one double)
+  void scalar_host_and(bool& v) {
+    double x = v ? 0.0 : 1.0;
+    CUDA_CHECK(cudaMemcpyAsync(scalar.p, &x, sizeof(double), cudaMemcpyHostToDevice, stream));
+    v = finish_scalar() == 0.0;
   }
   int rank() const { return comm ? comm->rank : 0; }
   int world() const { return comm ? comm->world : 1; }
@@ -583,6 +676,29 @@ struct amgb_hierarchy {
     const int g = rank(), G = world();
     const int up_cnt = plan.halo_hi[l];  // what rank g-1 keeps above its block = my first rows
     const int dn_cnt = plan.halo_lo[l];  // what rank g+1 keeps below its block = my last rows
+    ++halo_exchanges_per_vcycle;
+    if (p2p) {
+      const int v = (base == S.u.p) ? 0 : 1;
+      const int site = site_cursor++;
+      if (site >= kMaxSites) throw ApiError(AMGB_ESTATE, "too many halo-exchange sites");
+      dev::HaloSide lo{}, hi{};
+      if (g > 0) {  // my first rows -> rank g-1's upper halo
+        lo.peer_dst = peers[l].lo[v] + peers[l].lo_halo_lo + peers[l].lo_n_own;
+        lo.src = base + S.halo_lo;
+        lo.count = up_cnt;
+        lo.peer_flag = peer_flags_lo + 2 * site + 1;  // "bumped by your upper neighbour"
+        lo.my_flag = flags.p + 2 * site + 0;
+      }
+      if (g + 1 < G) {  // my last rows -> rank g+1's lower halo
+        hi.peer_dst = peers[l].hi[v];
+        hi.src = base + S.halo_lo + S.n_own - dn_cnt;
+        hi.count = dn_cnt;
+        hi.peer_flag = peer_flags_hi + 2 * site + 0;  // "bumped by your lower neighbour"
+        hi.my_flag = flags.p + 2 * site + 1;
+      }
+      LAUNCH(dev::k_halo_exchange, 2, 256, 0, s, lo, hi, epochs.p + 2 * site, timed_out.p);
+      return;
+    }
     NCCL_CHECK(nc.GroupStart());
     if (g > 0) {
       NCCL_CHECK(nc.Send(base + S.halo_lo, up_cnt, ncclDouble, g - 1, comm->comm, s));
@@ -593,7 +709,6 @@ struct amgb_hierarchy {
       NCCL_CHECK(nc.Recv(base + S.halo_lo + S.n_own, S.halo_hi, ncclDouble, g + 1, comm->comm, s));
     }
     NCCL_CHECK(nc.GroupEnd());
-    ++halo_exchanges_per_vcycle;
   }
   // every rank contributes its block [start[r], start[r+1]) of a full-length vector
   void allgather_blocks(double* full, const std::vector<int64_t>& start, cudaStream_t s) {
@@ -686,6 +801,7 @@ struct amgb_hierarchy {
 
   void enqueue_vcycle(cudaStream_t s) {
     halo_exchanges_per_vcycle = 0;
+    site_cursor = 0;  // sites 0 .. k-1 belong to the V-cycle, in the same order on every rank
     for (int l = 0; l < L; ++l) {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
@@ -739,7 +855,12 @@ struct amgb_hierarchy {
   }
   double rss() {
     LevelState& S = lv[0];
-    if (S.sharded) exchange(0, S.u.p, stream);
+    if (S.sharded) {
+      const int keep = site_cursor;
+      site_cursor = kMaxSites - 1;  // reserved site for exchanges outside the V-cycle
+      exchange(0, S.u.p, stream);
+      site_cursor = keep;
+    }
     ops[0]->rss(S.u_own(), S.f.p, partial.p, scalar.p, stream);
     return S.sharded ? finish_scalar() : finish_scalar_local();
   }
@@ -1126,6 +1247,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
   h->dd.upload(h->factor.d, s);
   h->dwork.alloc(h->factor.n);
   CUDA_CHECK(cudaStreamSynchronize(s));
+  h->setup_p2p();
   *out = h.release();
 }
 
@@ -1157,6 +1279,16 @@ int amgb_hierarchy_local_range(const amgb_hierarchy* h, int level, int64_t* begi
 }
 int64_t amgb_hierarchy_halo_exchanges_per_vcycle(const amgb_hierarchy* h) {
   return h ? h->halo_exchanges_per_vcycle : 0;
+}
+int amgb_hierarchy_halo_mode(const amgb_hierarchy* h) {
+  if (!h || h->n_sharded == 0) return AMGB_HALO_NONE;
+  return h->p2p ? AMGB_HALO_PEER : AMGB_HALO_NCCL;
+}
+int amgb_hierarchy_halo_timed_out(amgb_hierarchy* h) {
+  if (!h || !h->p2p) return 0;
+  int v = 0;
+  cudaMemcpy(&v, h->timed_out.p, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
 }
 
 // ---- communicator ----
@@ -1216,6 +1348,15 @@ int amgb_hierarchy_destroy(amgb_hierarchy* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->p2p) {
+      // collective: nobody unmaps or frees a vector a neighbour may still write into
+      bool ok = true;
+      h->stream = h->own_stream;
+      h->scalar_host_and(ok);
+      for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+      h->ipc_opened.clear();
+      h->scalar_host_and(ok);
+    }
     delete h;
   });
 }

@@ -475,6 +475,47 @@ __global__ void __launch_bounds__(256) k_prolong_add(const double* __restrict__ 
   u[t] = __dadd_rn(u[t], prolong_at(e, e_first, n_coarse, fine_first + t));
 }
 
+// ------------------------------------------------------------------ peer-memory halo exchange
+// One launch per exchange site.  Block 0 serves the lower neighbour (rank g-1), block 1 the
+// upper one: copy this rank's boundary rows straight into the neighbour's halo region
+// (peer-mapped pointer, stores travel over NVLink), make them visible system-wide, bump the
+// neighbour's epoch flag for this site, then wait until the neighbour has done the same for
+// us.  Epochs live in device memory so a replayed CUDA graph keeps counting.  A rank can be
+// at most one site ahead of its neighbours, and consecutive sites of one level alternate
+// between the two ping-pong vectors, so a halo is never overwritten while it is still read.
+struct HaloSide {
+  double* peer_dst;               // where my rows go in the neighbour's vector (nullptr: no neighbour)
+  const double* src;              // my boundary rows
+  int count;                      // doubles to send
+  unsigned long long* peer_flag;  // neighbour's flag for (site, the side I am on from its view)
+  unsigned long long* my_flag;    // my flag the neighbour bumps
+};
+__global__ void __launch_bounds__(256) k_halo_exchange(HaloSide lo, HaloSide hi, unsigned long long* epoch,
+                                                       int* timed_out) {
+  const HaloSide S = blockIdx.x == 0 ? lo : hi;
+  if (S.peer_dst == nullptr) return;
+  for (int i = threadIdx.x; i < S.count; i += blockDim.x) S.peer_dst[i] = S.src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long e = epoch[blockIdx.x] + 1;
+    epoch[blockIdx.x] = e;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(S.peer_flag), "l"(e) : "memory");
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(S.my_flag) : "memory");
+      if (seen >= e) break;
+      if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour died; do not hang the GPU
+        *timed_out = 1;
+        break;
+      }
+      __nanosleep(40);
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ rss = sum (b - A u)^2
 // bhat_i accumulates from +0 in ascending column order, d = b_i - bhat_i
 // (common.hpp:21-25).  The outer sum is a fixed-shape tree (deterministic; it

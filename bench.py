@@ -316,9 +316,12 @@ def run_b200(a):
                    "l2_policy": "inputs larger than L2 (level-0 operator+vectors stream %.2f GB per "
                                 "pass, L2 is 126 MB)" % (bytes0 / 1e9),
                    "parallelism": "single GPU" if world == 1 else
-                                  "row blocks x%d, %d sharded levels, NCCL halo send/recv (%d exchanges per "
+                                  "row blocks x%d, %d sharded levels, halo exchange via %s (%d exchanges per "
                                   "V-cycle), coarser levels replicated after one gather" % (
-                                      world, mg.n_sharded_levels(), mg.halo_exchanges_per_vcycle()),
+                                      world, mg.n_sharded_levels(),
+                                      {"peer": "peer-memory writes over NVLink + epoch flags",
+                                       "nccl": "NCCL send/recv"}.get(mg.halo_mode(), mg.halo_mode()),
+                                      mg.halo_exchanges_per_vcycle()),
                    "mdof_per_s": vps * N0 / 1e6, "setup_s": setup_s,
                    "rss_after_timed_cycles": rss_after,
                    "vcycle_layout_bytes": layout_bytes,

@@ -175,6 +175,16 @@ int amgb_hierarchy_n_sharded_levels(const amgb_hierarchy* h);
 /* rows [begin, end) of `level` this rank owns (the whole level when it is not sharded) */
 int amgb_hierarchy_local_range(const amgb_hierarchy* h, int level, int64_t* begin, int64_t* end);
 int64_t amgb_hierarchy_halo_exchanges_per_vcycle(const amgb_hierarchy* h);
+/* How halos travel.  PEER: one kernel per exchange writes the boundary rows straight into
+ * the neighbours' halo buffers (CUDA-IPC mapped peer memory over NVLink) and spins on an
+ * epoch flag; NCCL: grouped ncclSend/ncclRecv (fallback when IPC mapping is unavailable, or
+ * forced with the environment variable AMGB_HALO=nccl). */
+#define AMGB_HALO_NONE 0
+#define AMGB_HALO_NCCL 1
+#define AMGB_HALO_PEER 2
+int amgb_hierarchy_halo_mode(const amgb_hierarchy* h);
+/* 1 if a peer-memory exchange ever gave up waiting for a neighbour (results are invalid) */
+int amgb_hierarchy_halo_timed_out(amgb_hierarchy* h);
 /* host only: the plan a sharded hierarchy uses.  starts has n_levels*(world+1) slots
  * (row l holds the world+1 block boundaries of level l), the other arrays n_levels. */
 int amgb_partition_plan(int n_levels, const int64_t* level_sizes, const int* half_bandwidth,

@@ -43,6 +43,8 @@ def main():
                                use_graph=use_graph)
             ns = mg.n_sharded_levels()
             assert ns >= 2, ns
+            want_mode = os.environ.get("AMGB_HALO", "peer")
+            assert mg.halo_mode() == want_mode, (mg.halo_mode(), want_mode)
             single = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1)
             for _ in range(3):
                 mg.vcycle()
@@ -50,6 +52,7 @@ def main():
             for l in range(L):
                 got, want = mg.get_soln(l), single.get_soln(l)
                 assert got.tobytes() == want.tobytes(), (n, l, use_graph, np.abs(got - want).max())
+            assert not mg.halo_timed_out()
             r_sh, r_one = mg.rss(), single.rss()
             assert abs(r_sh - r_one) <= 1e-13 * r_one, (r_sh, r_one)
             if rank == 0 and n <= 600 and not use_graph:
@@ -60,8 +63,8 @@ def main():
             else:
                 mg.get_soln(0)  # collective: every rank takes part
             if rank == 0:
-                print("ok n=%d levels=%d sharded_levels=%d graph=%s halo_exchanges/vcycle=%d rss=%.6e" % (
-                    n, L, ns, use_graph, mg.halo_exchanges_per_vcycle(), r_sh), flush=True)
+                print("ok n=%d levels=%d sharded_levels=%d graph=%s halo=%s exchanges/vcycle=%d rss=%.6e" % (
+                    n, L, ns, use_graph, mg.halo_mode(), mg.halo_exchanges_per_vcycle(), r_sh), flush=True)
             del mg, single
     dist.barrier()
     del comm
