@@ -31,7 +31,7 @@ class Options(C.Structure):
                 ("compute_error_every_n_iters", _l), ("n_iters", _l),
                 ("smoother", _i), ("smoother_iters", _l), ("omega", _d),
                 ("gs_mode", _i), ("use_graph", _i),
-                ("skip_dead_coarse_smooth", _i)]
+                ("skip_dead_coarse_smooth", _i), ("fuse", _i)]
 
 
 class AmgbError(RuntimeError):
@@ -390,7 +390,7 @@ class Multigrid:
 
     def __init__(self, interpolator, smoother, A, b, n_levels, tolerance=1e-9,
                  compute_error_every_n_iters=10, n_iters=100, use_graph=True,
-                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18):
+                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18, fuse=True):
         self.interpolator, self.smoother = interpolator, smoother
         o = Options()
         lib().amgb_options_default(C.byref(o))
@@ -404,6 +404,7 @@ class Multigrid:
         o.gs_mode = getattr(smoother, "mode", GS_AUTO)
         o.use_graph = int(use_graph)
         o.skip_dead_coarse_smooth = int(skip_dead_coarse_smooth)
+        o.fuse = int(fuse)
         b = _f64(b)
         h = _p()
         if comm is None:

@@ -426,6 +426,36 @@ struct Operator {
       LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, omega, out);
     });
   }
+  // first sweep from u = 0: only f and the diagonal are read (DIA); other layouts run the
+  // ordinary sweep on an explicitly zeroed u
+  bool jacobi_from_zero(const double* f, double omega, double* out, cudaStream_t s) const {
+    const DevMat& A = rows_of_A();
+    if (!n || !A.is_dia) return false;
+    int diag_d = -1;
+    for (int d = 0; d < A.dia.n_diag; ++d)
+      if (A.dia.off[d] == 0) diag_d = d;
+    if (diag_d < 0) return false;
+    with_view(A, [&](auto V) { launch_jacobi_zero(V, diag_d, f, omega, out, s); });
+    return true;
+  }
+  template <int ND>
+  void launch_jacobi_zero(dev::DiaViewT<ND> V, int diag_d, const double* f, double omega, double* out,
+                          cudaStream_t s) const {
+    auto kern = dev::k_jacobi_zero<ND>;
+    V.n_rows = n;
+    LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, diag_d, f, omega, out);
+  }
+  void launch_jacobi_zero(SellView, int, const double*, double, double*, cudaStream_t) const {}
+  // first post-smoothing sweep on u + P e without materialising it
+  void jacobi_prolong(const double* u, const double* e, int e_first, int n_coarse, int fine_first,
+                      const double* f, double omega, double* out, cudaStream_t s) const {
+    if (!n) return;
+    with_view(rows_of_A(), [&](auto V) {
+      auto kern = dev::k_jacobi_prolong<decltype(V)>;
+      V.n_rows = n;
+      LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, e, e_first, n_coarse, fine_first, f, omega, out);
+    });
+  }
   void color_pass(int c, const double* f, double* u, cudaStream_t s) const {
     const DevMat& C = *color_sell[c];
     if (!C.n_rows()) return;
@@ -481,6 +511,7 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
+  o->fuse = 1;
 }
 
 }  // namespace
@@ -723,32 +754,54 @@ struct amgb_hierarchy {
   }
 
   // smoother->smooth(A_l, u_l, f_l)   (multigrid.hpp:268-269, :300-301)
-  void smooth(int l, cudaStream_t s) {
+  // from_zero:   u_l is known to be zero (pre-smoothing of a coarse level, :278)
+  // with_prolong: the coarse-grid correction u_l += P u_{l+1} (:294-296) has not been applied
+  //               yet and is folded into the first sweep (Jacobi) or applied first (others)
+  void smooth(int l, cudaStream_t s, bool from_zero = false, bool with_prolong = false) {
     Operator& A = *ops[l];
     LevelState& S = lv[l];
     const int64_t iters = opt.smoother_iters;
-    if (opt.smoother == AMGB_SMOOTHER_GS) {
-      for (int64_t it = 0; it < iters; ++it) {  // smoother.hpp:195-198
-        A.gs_direction(true, S.f.p, S.u.p, S.tmp.p, opt.gs_mode, s);
-        A.gs_direction(false, S.f.p, S.u.p, S.tmp.p, opt.gs_mode, s);
+    if (opt.smoother != AMGB_SMOOTHER_JACOBI || iters < 1) {
+      if (with_prolong) prolong_add(l, s);
+      if (opt.smoother == AMGB_SMOOTHER_GS) {
+        for (int64_t it = 0; it < iters; ++it) {  // smoother.hpp:195-198
+          A.gs_direction(true, S.f.p, S.u.p, S.tmp.p, opt.gs_mode, s);
+          A.gs_direction(false, S.f.p, S.u.p, S.tmp.p, opt.gs_mode, s);
+        }
+      } else if (opt.smoother == AMGB_SMOOTHER_COLOR_GS) {
+        for (int64_t it = 0; it < iters; ++it) {
+          for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, S.f.p, S.u.p, s);
+          for (int c = A.n_colors - 1; c >= 0; --c) A.color_pass(c, S.f.p, S.u.p, s);
+        }
       }
-    } else if (opt.smoother == AMGB_SMOOTHER_JACOBI) {
-      double* src = S.u.p;
-      double* dst = S.tmp.p;
-      for (int64_t it = 0; it < iters; ++it) {
+      return;
+    }
+    double* src = S.u.p;
+    double* dst = S.tmp.p;
+    for (int64_t it = 0; it < iters; ++it) {
+      bool done = false;
+      if (it == 0 && from_zero && opt.fuse) {
+        done = A.jacobi_from_zero(S.f.p, opt.omega, dst + S.halo_lo, s);
+      } else if (it == 0 && with_prolong && opt.fuse) {
+        // u_l's halos are still current (u_l has not changed since the down-leg exchange);
+        // the coarse halos are exchanged here
+        LevelState& C = lv[l + 1];
+        if (C.sharded) exchange(l + 1, C.u.p, s);
+        const int e_first = C.sharded ? (int)(C.s - C.halo_lo) : 0;
+        A.jacobi_prolong(src + S.halo_lo, C.u.p, e_first, (int)n[l + 1], (int)S.s, S.f.p, opt.omega,
+                         dst + S.halo_lo, s);
+        done = true;
+      }
+      if (!done) {
+        if (it == 0 && with_prolong) prolong_add(l, s);
         exchange(l, src, s);
         A.jacobi(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, s);
-        std::swap(src, dst);
       }
-      if (src != S.u.p)
-        CUDA_CHECK(cudaMemcpyAsync(S.u_own(), src + S.halo_lo, sizeof(double) * S.n_own,
-                                   cudaMemcpyDeviceToDevice, s));
-    } else {
-      for (int64_t it = 0; it < iters; ++it) {
-        for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, S.f.p, S.u.p, s);
-        for (int c = A.n_colors - 1; c >= 0; --c) A.color_pass(c, S.f.p, S.u.p, s);
-      }
+      std::swap(src, dst);
     }
+    if (src != S.u.p)
+      CUDA_CHECK(cudaMemcpyAsync(S.u_own(), src + S.halo_lo, sizeof(double) * S.n_own,
+                                 cudaMemcpyDeviceToDevice, s));
   }
   // f_{l+1} = R_l (f_l - A_l u_l), u_{l+1} = 0   (multigrid.hpp:272-282)
   void residual_restrict(int l, cudaStream_t s) {
@@ -805,16 +858,13 @@ struct amgb_hierarchy {
     for (int l = 0; l < L; ++l) {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
-      smooth(l, s);
+      smooth(l, s, /*from_zero=*/l > 0);
       if (!coarsest) residual_restrict(l, s);
       // on the coarsest level the reference also forms the residual (:272-274);
       // it is stored in a private member without a getter and never read.
     }
     coarse_solve(s);
-    for (int l = L - 2; l >= 0; --l) {
-      prolong_add(l, s);
-      smooth(l, s);
-    }
+    for (int l = L - 2; l >= 0; --l) smooth(l, s, false, /*with_prolong=*/true);
   }
   void build_graph() {
     if (exec) return;

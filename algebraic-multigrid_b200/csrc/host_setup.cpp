@@ -360,7 +360,7 @@ PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
     int ghost = 0;
     for (int l = ns - 1; l >= 0 && ok; --l) {
       ghost = 2 * ghost + 1;
-      const int64_t need = 4ll * (half_bandwidth[l] + ghost) + (1ll << ns);
+      const int64_t need = 4ll * (half_bandwidth[l] + ghost + 2) + (1ll << ns);
       if (level_sizes[l] / world < need) ok = false;
     }
     if (ok) break;
@@ -382,8 +382,10 @@ PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
   for (int l = ns - 1; l >= 0; --l) {
     ghost = 2 * ghost + 1;
     P.ghost[l] = ghost;
-    P.halo_lo[l] = half_bandwidth[l];
-    P.halo_hi[l] = half_bandwidth[l] + ghost;
+    // +2: the fused prolongation sweep evaluates u + P e on the fine halo, which reaches one
+    // coarse entry further than the coarse operator's own half-bandwidth
+    P.halo_lo[l] = half_bandwidth[l] + 2;
+    P.halo_hi[l] = half_bandwidth[l] + ghost + 2;
   }
   return P;
 }

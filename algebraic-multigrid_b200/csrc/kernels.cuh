@@ -50,23 +50,27 @@ struct DiaViewT : DiaView {};
 // Visit the entries of DIA row t (matrix row `row`) in ascending column order.
 // All val loads and all x gathers are independent of each other (x index =
 // row + off, clamped; an absent entry has val == 0 and is skipped).
-template <int ND, class Fn>
-__device__ __forceinline__ void for_each_entry(const DiaViewT<ND>& S, int t, int row, const double* x, Fn&& fn) {
+template <int ND, class XLoad, class Fn>
+__device__ __forceinline__ void for_each_entry_x(const DiaViewT<ND>& S, int t, int row, XLoad&& xload, Fn&& fn) {
   const double* vp = S.val + t;
   double v[ND], xv[ND];
 #pragma unroll
   for (int d = 0; d < ND; ++d) v[d] = (d < S.n_diag) ? vp[(size_t)d * S.ld] : 0.0;
 #pragma unroll
-  for (int d = 0; d < ND; ++d) xv[d] = (d < S.n_diag) ? x[min(max(row + S.off[d], S.c_min), S.c_max)] : 0.0;
+  for (int d = 0; d < ND; ++d) xv[d] = (d < S.n_diag) ? xload(min(max(row + S.off[d], S.c_min), S.c_max)) : 0.0;
 #pragma unroll
   for (int d = 0; d < ND; ++d)
     if (v[d] != 0.0) fn(row + S.off[d], v[d], xv[d]);
 }
+template <int ND, class Fn>
+__device__ __forceinline__ void for_each_entry(const DiaViewT<ND>& S, int t, int row, const double* x, Fn&& fn) {
+  for_each_entry_x(S, t, row, [&](int c) { return x[c]; }, fn);
+}
 
 // Visit the entries of SELL row t in ascending column order.  Loads are
 // batched four at a time (4 col + 4 val loads in flight, then 4 gathers).
-template <class Fn>
-__device__ __forceinline__ void for_each_entry(const SellView& S, int t, int /*row*/, const double* x, Fn&& fn) {
+template <class XLoad, class Fn>
+__device__ __forceinline__ void for_each_entry_x(const SellView& S, int t, int /*row*/, XLoad&& xload, Fn&& fn) {
   const int s = t >> 5;
   const uint32_t begin = S.slice_ptr[s] + (t & 31);
   const uint32_t end = S.slice_ptr[s + 1];
@@ -84,11 +88,15 @@ __device__ __forceinline__ void for_each_entry(const SellView& S, int t, int /*r
       v[k] = (c[k] >= 0) ? S.val[q] : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xv[k] = (c[k] >= 0) ? x[c[k]] : 0.0;
+    for (int k = 0; k < 4; ++k) xv[k] = (c[k] >= 0) ? xload(c[k]) : 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (c[k] >= 0) fn(c[k], v[k], xv[k]);
   }
+}
+template <class Fn>
+__device__ __forceinline__ void for_each_entry(const SellView& S, int t, int row, const double* x, Fn&& fn) {
+  for_each_entry_x(S, t, row, [&](int c) { return x[c]; }, fn);
 }
 
 // ((f - a1 x1) - a2 x2) - ...   (multigrid.hpp:272-274)
@@ -111,6 +119,52 @@ __device__ __forceinline__ double row_gs(const M& S, int t, int row, const doubl
     else rsum = __dadd_rn(rsum, __dmul_rn(a, xv));
   });
   return (diag == 0.0) ? keep : __ddiv_rn(__dsub_rn(b, rsum), diag);
+}
+
+// i: global fine row; e[J - e_first] holds coarse entry J (e_first = global index of e[0],
+// non-zero when the coarse vector is a halo-extended row block).
+__device__ __forceinline__ double prolong_at(const double* __restrict__ e, int e_first, int n_coarse, int i) {
+  double acc = 0.0;
+  const int J = i >> 1;
+  if (i & 1) {
+    if (J >= 0 && J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(1.0, e[J - e_first]));
+  } else {
+    if (J - 1 >= 0 && J - 1 < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - 1 - e_first]));
+    if (J >= 0 && J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - e_first]));
+  }
+  return acc;
+}
+// ------------------------------------------------------------------ damped Jacobi, fused variants
+// First sweep from a zero initial guess (every coarse level starts its pre-smoothing from
+// u = 0, multigrid.hpp:278): r = f - A*0 = f exactly, so u_new = 0 + omega*(f/d) = omega*(f/d)
+// bit for bit, and neither the operator nor u is read.
+template <int ND>
+__global__ void __launch_bounds__(256) k_jacobi_zero(DiaViewT<ND> A, int diag_d, const double* __restrict__ f,
+                                                     double omega, double* __restrict__ u_new) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_rows) return;
+  const double diag = A.val[(size_t)diag_d * A.ld + t];
+  u_new[t] = (diag == 0.0) ? 0.0 : __dmul_rn(omega, __ddiv_rn(f[t], diag));
+}
+
+// First post-smoothing sweep fused with the coarse-grid correction (multigrid.hpp:294-301):
+// the sweep runs on u' = u + P e, with u'[c] = u[c] + (P e)[c] formed on the fly for every
+// entry it reads, so u' is never written to memory.  fine_first = global row of u[0].
+template <class M>
+__global__ void __launch_bounds__(256) k_jacobi_prolong(M A, const double* __restrict__ u,
+                                                        const double* __restrict__ e, int e_first, int n_coarse,
+                                                        int fine_first, const double* __restrict__ f, double omega,
+                                                        double* __restrict__ u_new) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_rows) return;
+  auto corrected = [&](int c) { return __dadd_rn(u[c], prolong_at(e, e_first, n_coarse, fine_first + c)); };
+  double acc = f[t], diag = 0.0;
+  for_each_entry_x(A, t, t, corrected, [&](int c, double a, double xv) {
+    if (c == t) diag = a;
+    acc = __dsub_rn(acc, __dmul_rn(a, xv));
+  });
+  const double ut = corrected(t);
+  u_new[t] = (diag == 0.0) ? ut : __dadd_rn(ut, __dmul_rn(omega, __ddiv_rn(acc, diag)));
 }
 
 // ------------------------------------------------------------------ residual
@@ -432,7 +486,7 @@ __global__ void __launch_bounds__(256) k_residual_restrict(M A, const double* __
       const double a = __dmul_rn(0.5, r[2 * t]);
       const double b = __dadd_rn(a, r[2 * t + 1]);
       f_coarse[J] = __dadd_rn(b, __dmul_rn(0.5, r[2 * t + 2]));
-      u_coarse[J] = 0.0;
+      if (u_coarse) u_coarse[J] = 0.0;
     }
   }
 }
@@ -454,19 +508,6 @@ __global__ void __launch_bounds__(256) k_restrict(const double* __restrict__ r, 
 // u[i] = u[i] + (P e)[i]; (P e)[2J+1] = 0 + 1 e[J]; (P e)[2J] = (0 + .5 e[J-1]) + .5 e[J]
 // with the terms whose coarse index is outside [0, n_coarse) absent
 // (interpolator.hpp:52-56,118-125; multigrid.hpp:294-296).
-// i: global fine row; e[J - e_first] holds coarse entry J (e_first = global index of e[0],
-// non-zero when the coarse vector is a halo-extended row block).
-__device__ __forceinline__ double prolong_at(const double* __restrict__ e, int e_first, int n_coarse, int i) {
-  double acc = 0.0;
-  const int J = i >> 1;
-  if (i & 1) {
-    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(1.0, e[J - e_first]));
-  } else {
-    if (J - 1 >= 0 && J - 1 < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - 1 - e_first]));
-    if (J < n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, e[J - e_first]));
-  }
-  return acc;
-}
 // u points at this rank's first owned fine row (global row fine_first), n_own rows.
 __global__ void __launch_bounds__(256) k_prolong_add(const double* __restrict__ e, int e_first, int n_coarse,
                                                      double* __restrict__ u, int fine_first, int n_own) {
