@@ -364,7 +364,7 @@ def test_fused_jacobi_cycle_is_bit_identical(n, L, eps):
 
 
 def test_relative_residual_criterion():
-    mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel(), every=1, n_iters=200)
+    mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel(mode=amg.GS_LEVELSCHED), every=1, n_iters=200)
     A, b, Ao = problem(35)
     mg.solve_relative(1e-8)
     k = mg.iters_done
