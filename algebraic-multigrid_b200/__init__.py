@@ -390,7 +390,7 @@ class Multigrid:
 
     def __init__(self, interpolator, smoother, A, b, n_levels, tolerance=1e-9,
                  compute_error_every_n_iters=10, n_iters=100, use_graph=True,
-                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18, fuse=True):
+                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18, fuse=1):
         self.interpolator, self.smoother = interpolator, smoother
         o = Options()
         lib().amgb_options_default(C.byref(o))

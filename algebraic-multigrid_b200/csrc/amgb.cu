@@ -483,7 +483,9 @@ struct Operator {
     with_view(rows_of_A(), [&](auto V) {
       auto kern = dev::k_residual_restrict<decltype(V)>;
       V.n_rows = n_mat;
-      LAUNCH(kern, blocks_for(n_mat, 256), 256, 0, s, V, u, f, f_coarse, u_coarse, n_coarse);
+      if (n_coarse > 0)
+        LAUNCH(kern, blocks_for(n_coarse, dev::kRRCoarsePerBlock), 256, 0, s, V, u, f, f_coarse, u_coarse,
+               n_coarse);
     });
   }
   int rss_blocks() const { return std::max(1, blocks_for(n, 256)); }
@@ -511,7 +513,7 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
-  o->fuse = 1;
+  o->fuse = 1;  // zero-guess sweep on; prolongation fusion (bit 1) measured slower
 }
 
 }  // namespace
@@ -575,7 +577,7 @@ struct amgb_hierarchy {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int64_t launches_per_vcycle = 0;
-  bool ldlt_attr_set = false;
+  bool ldlt_attr_set = false, ldlt_warp_attr_set = false;
   int64_t iters_done = 0;
   std::vector<double> history;
   // sharding
@@ -780,9 +782,9 @@ struct amgb_hierarchy {
     double* dst = S.tmp.p;
     for (int64_t it = 0; it < iters; ++it) {
       bool done = false;
-      if (it == 0 && from_zero && opt.fuse) {
+      if (it == 0 && from_zero && (opt.fuse & 1)) {
         done = A.jacobi_from_zero(S.f.p, opt.omega, dst + S.halo_lo, s);
-      } else if (it == 0 && with_prolong && opt.fuse) {
+      } else if (it == 0 && with_prolong && (opt.fuse & 2)) {
         // u_l's halos are still current (u_l has not changed since the down-leg exchange);
         // the coarse halos are exchanged here
         LevelState& C = lv[l + 1];
@@ -839,6 +841,18 @@ struct amgb_hierarchy {
     const size_t xbytes = sizeof(double) * (size_t)nc;
     const size_t lbytes = sizeof(double) * (size_t)nc * std::max(bw, 1);
     const size_t cap = 200 * 1024;
+    if (bw <= 31 && xbytes <= cap) {
+      const int l_smem = xbytes + lbytes <= cap;
+      const size_t smem = xbytes + (l_smem ? lbytes : 0);
+      if (smem > 48 * 1024 && !ldlt_warp_attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(dev::k_banded_ldlt_solve_warp,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        ldlt_warp_attr_set = true;
+      }
+      LAUNCH(dev::k_banded_ldlt_solve_warp, 1, 32, smem, s, dL.p, dd.p, nc, bw, lv[L - 1].f.p, lv[L - 1].u.p,
+             l_smem);
+      return;
+    }
     const int x_smem = xbytes <= cap;
     const int l_smem = x_smem && xbytes + lbytes <= cap;
     const size_t smem = (x_smem ? xbytes : 0) + (l_smem ? lbytes : 0);

@@ -463,25 +463,24 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
 // ------------------------------------------------------------------ fused residual + restriction
 // f_c[J] = ((0 + .5 r[2J]) + 1 r[2J+1]) + .5 r[2J+2]  with r = f - A u never
 // written to HBM; also zeroes the coarse solution (multigrid.hpp:272-282).
-// A block owns 256 fine rows and the 128 coarse rows centred in them; the one
-// extra fine row 2J+2 of its last coarse row is recomputed by thread 0.
+// (The first fine row of the view must be an even global row.)
+// A block computes 256 consecutive fine residuals starting at fine row 252*b and emits the
+// 126 coarse rows 126*b .. 126*b+125, whose three fine rows all lie inside; consecutive
+// blocks overlap by four fine rows (1.6 % redundant work) so no thread does a second row.
+constexpr int kRRCoarsePerBlock = 126;
 template <class M>
 __global__ void __launch_bounds__(256) k_residual_restrict(M A, const double* __restrict__ u,
                                                            const double* __restrict__ f,
                                                            double* __restrict__ f_coarse,
                                                            double* __restrict__ u_coarse, int n_coarse) {
-  __shared__ double r[257];
-  const int base = blockIdx.x * 256;
+  __shared__ double r[256];
+  const int base = blockIdx.x * (2 * kRRCoarsePerBlock);
   const int t = threadIdx.x;
   const int row = base + t;
   r[t] = (row < A.n_rows) ? row_residual(A, row, row, u, f[row]) : 0.0;
-  if (t == 0) {
-    const int extra = base + 256;
-    r[256] = (extra < A.n_rows) ? row_residual(A, extra, extra, u, f[extra]) : 0.0;
-  }
   __syncthreads();
-  if (t < 128) {
-    const int J = (base >> 1) + t;
+  if (t < kRRCoarsePerBlock) {
+    const int J = blockIdx.x * kRRCoarsePerBlock + t;
     if (J < n_coarse) {
       const double a = __dmul_rn(0.5, r[2 * t]);
       const double b = __dadd_rn(a, r[2 * t + 1]);
@@ -648,6 +647,55 @@ __global__ void __launch_bounds__(1024) k_banded_ldlt_solve(const double* __rest
     __syncthreads();
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) x_out[i] = x[i];
+}
+
+// Same solve for half-bandwidth <= 31, run by ONE warp with the active part of the vector
+// held in a register window (lane j holds the partial value of row pivot+j): per pivot one
+// broadcast shuffle, one multiply-subtract and one shift shuffle, the factor entries and the
+// entering element being read ahead of the dependent chain.  The order in which each entry
+// receives its updates is that of k_banded_ldlt_solve, so the bits are the same.
+__global__ void __launch_bounds__(32) k_banded_ldlt_solve_warp(const double* __restrict__ L,
+                                                               const double* __restrict__ d, int n, int bw,
+                                                               const double* __restrict__ f,
+                                                               double* __restrict__ x_out, int L_in_smem) {
+  extern __shared__ double sm[];
+  double* y = sm;  // n
+  const int lane = threadIdx.x;
+  const int ld = bw > 0 ? bw : 1;
+  const double* Lp = L;
+  if (L_in_smem) {
+    double* sL = sm + n;
+    for (size_t i = lane; i < (size_t)n * ld; i += 32) sL[i] = L[i];
+    Lp = sL;
+  }
+  __syncwarp();
+  // forward: window lane j = partial x[i + j]
+  double w = (lane < n) ? f[lane] : 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int r = i + lane;
+    const double lij = (lane >= 1 && lane <= bw && r < n) ? Lp[(size_t)r * ld + (bw - lane)] : 0.0;
+    const double enter = (i + 32 < n) ? f[i + 32] : 0.0;
+    const double xi = __shfl_sync(0xffffffffu, w, 0);
+    if (lane == 0) y[i] = xi;
+    if (lane >= 1 && lane <= bw && r < n) w = __dsub_rn(w, __dmul_rn(lij, xi));
+    w = __shfl_down_sync(0xffffffffu, w, 1);
+    if (lane == 31) w = enter;
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) y[i] = __ddiv_rn(y[i], d[i]);
+  __syncwarp();
+  // backward: window lane j = partial z[i - j]
+  w = (n - 1 - lane >= 0) ? y[n - 1 - lane] : 0.0;
+  for (int i = n - 1; i >= 0; --i) {
+    const int c = i - lane;
+    const double lic = (lane >= 1 && lane <= bw && c >= 0) ? Lp[(size_t)i * ld + (bw - lane)] : 0.0;
+    const double enter = (i - 32 >= 0) ? y[i - 32] : 0.0;
+    const double xi = __shfl_sync(0xffffffffu, w, 0);
+    if (lane == 0) x_out[i] = xi;
+    if (lane >= 1 && lane <= bw && c >= 0) w = __dsub_rn(w, __dmul_rn(lic, xi));
+    w = __shfl_down_sync(0xffffffffu, w, 1);
+    if (lane == 31) w = enter;
+  }
 }
 
 }  // namespace dev

@@ -139,9 +139,10 @@ typedef struct amgb_options {
   int skip_dead_coarse_smooth; /* 1: drop the pre-smooth + residual the reference
                                does on the coarsest level and then overwrites
                                (multigrid.hpp:265-274 vs :287-288); unobservable   */
-  int fuse;                 /* 1 (default): damped-Jacobi cycles skip the operator read of
-                               the first pre-smoothing sweep on coarse levels (u = 0 there)
-                               and fold u += P e into the first post-smoothing sweep; the
+  int fuse;                 /* bit 0 (default on): damped-Jacobi cycles skip the operator read
+                               of the first pre-smoothing sweep on coarse levels (u = 0
+                               there); bit 1 (default off: measured slower, profiles/):
+                               fold u += P e into the first post-smoothing sweep.  The
                                arithmetic, hence every bit of the result, is unchanged   */
 } amgb_options;
 void amgb_options_default(amgb_options* opt);

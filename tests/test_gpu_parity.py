@@ -351,13 +351,15 @@ def test_dead_coarse_smooth_is_unobservable_and_graph_equals_stream():
 def test_fused_jacobi_cycle_is_bit_identical(n, L, eps):
     """The zero-guess first sweep and the prolongation fused into the first post-smoothing
     sweep only skip memory traffic; every bit of every level must be unchanged."""
-    fused, mo, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), eps)
-    plain, _, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), eps, fuse=False)
-    odd, mo3, _ = make_pair(n, L, amg.DampedJacobi(0.6, 3), eps)
+    fused, mo, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), eps, fuse=3)
+    default, _, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), eps)
+    plain, _, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), eps, fuse=0)
+    odd, mo3, _ = make_pair(n, L, amg.DampedJacobi(0.6, 3), eps, fuse=3)
     for _ in range(3):
-        fused.vcycle(); plain.vcycle(); mo.vcycle(); odd.vcycle(); mo3.vcycle()
+        fused.vcycle(); default.vcycle(); plain.vcycle(); mo.vcycle(); odd.vcycle(); mo3.vcycle()
     for l in range(L):
         assert fused.get_soln(l).tobytes() == plain.get_soln(l).tobytes()
+        assert default.get_soln(l).tobytes() == plain.get_soln(l).tobytes()
         assert fused.get_soln(l).tobytes() == mo.u(l).tobytes()
         assert odd.get_soln(l).tobytes() == mo3.u(l).tobytes()
     assert fused.launches_per_vcycle() < plain.launches_per_vcycle()
