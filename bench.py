@@ -179,6 +179,7 @@ def run_b200(a):
     comm = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
         def exchange_id(raw):
