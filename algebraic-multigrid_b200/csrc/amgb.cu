@@ -142,7 +142,15 @@ struct DevDia {
   int off[dev::kMaxDiagDev] = {0};
   DevBuf<double> val;
   DevBuf<int> rows;
+  DevBuf<unsigned short> mask;
+  int64_t live_bytes = 0;  // matrix bytes a pass streams (masked-out slices excluded)
   void upload(const Dia& D, cudaStream_t s) {
+    live_bytes = (int64_t)D.val.size() * 8;
+    if (!D.mask.empty()) {
+      mask.upload(D.mask, s);
+      live_bytes = (int64_t)D.mask.size() * 2;
+      for (unsigned short m : D.mask) live_bytes += 256ll * __builtin_popcount(m);
+    }
     n_rows = D.n_rows;
     c_min = 0;
     c_max = D.n_cols - 1;
@@ -164,6 +172,7 @@ struct DevDia {
     for (int d = 0; d < dev::kMaxDiagDev; ++d) v.off[d] = off[d];
     v.val = val.p;
     v.rows = rows.p;
+    v.mask = mask.p;
     return v;
   }
 };
@@ -184,7 +193,7 @@ struct DevMat {
   int64_t nnz() const { return is_dia ? dia.nnz : sell.nnz; }
   // bytes of matrix data one pass streams
   int64_t stored_bytes() const {
-    return is_dia ? (int64_t)dia.val.n * 8 + (int64_t)dia.rows.n * 4
+    return is_dia ? dia.live_bytes + (int64_t)dia.rows.n * 4
                   : (int64_t)sell.val.n * 12 + (int64_t)sell.slice_ptr.n * 4 + (int64_t)sell.rows.n * 4;
   }
 };
@@ -729,7 +738,7 @@ struct amgb_hierarchy {
         hi.peer_flag = peer_flags_hi + 2 * site + 0;  // "bumped by your lower neighbour"
         hi.my_flag = flags.p + 2 * site + 1;
       }
-      LAUNCH(dev::k_halo_exchange, 2, 256, 0, s, lo, hi, epochs.p + 2 * site, timed_out.p);
+      LAUNCH(dev::k_halo_exchange, 2, 1024, 0, s, lo, hi, epochs.p + 2 * site, timed_out.p);
       return;
     }
     NCCL_CHECK(nc.GroupStart());
@@ -832,8 +841,12 @@ struct amgb_hierarchy {
     LevelState& C = lv[l + 1];
     if (C.sharded) exchange(l + 1, C.u.p, s);  // needs e[s_c - 1]
     const int e_first = C.sharded ? (int)(C.s - C.halo_lo) : 0;
-    LAUNCH(dev::k_prolong_add, blocks_for(F.n_own, 256), 256, 0, s, C.u.p, e_first, (int)n[l + 1],
-           F.u_own(), (int)F.s, F.n_own);
+    if ((reinterpret_cast<uintptr_t>(F.u_own()) & 15) == 0 && (F.s & 1) == 0)
+      LAUNCH(dev::k_prolong_add2, blocks_for((F.n_own + 1) / 2, 256), 256, 0, s, C.u.p, e_first, (int)n[l + 1],
+             F.u_own(), (int)F.s, F.n_own);
+    else
+      LAUNCH(dev::k_prolong_add, blocks_for(F.n_own, 256), 256, 0, s, C.u.p, e_first, (int)n[l + 1],
+             F.u_own(), (int)F.s, F.n_own);
   }
   void coarse_solve(cudaStream_t s) {  // multigrid.hpp:287-288
     const int nc = factor.n, bw = factor.bw;
@@ -1717,7 +1730,7 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
           A.residual_restrict(scratch_u.p, S.f.p, scratch_c2.p, scratch_c.p, (int)h->n[level + 1], s);
           break;
         case 3:
-          LAUNCH(dev::k_prolong_add, blocks_for(h->n[level], 256), 256, 0, s, scratch_c.p, 0,
+          LAUNCH(dev::k_prolong_add2, blocks_for((h->n[level] + 1) / 2, 256), 256, 0, s, scratch_c.p, 0,
                  (int)h->n[level + 1], scratch_u.p, 0, (int)h->n[level]);
           break;
         default:

@@ -330,6 +330,21 @@ Dia build_dia(const Csc& M, const std::vector<int>* rows) {
       D.val[static_cast<size_t>(d) * ld + t] = M.val[p];
     }
   }
+  // per-slice occupancy of each diagonal
+  const int n_slices = ld / 32;
+  std::vector<unsigned short> mask(n_slices, 0);
+  int64_t live = 0;
+  for (int d = 0; d < D.n_diag; ++d)
+    for (int s = 0; s < n_slices; ++s) {
+      const double* v = &D.val[static_cast<size_t>(d) * ld + 32 * static_cast<size_t>(s)];
+      bool any = false;
+      for (int k = 0; k < 32 && !any; ++k) any = (v[k] != 0.0);
+      if (any) {
+        mask[s] |= static_cast<unsigned short>(1u << d);
+        ++live;
+      }
+    }
+  if (live * 10 <= static_cast<int64_t>(D.n_diag) * n_slices * 9) D.mask = std::move(mask);
   return D;
 }
 

@@ -86,6 +86,9 @@ struct Dia {
   std::vector<int> off;
   std::vector<double> val;  // n_diag * ld
   std::vector<int> rows;    // optional row subset
+  // bit d of mask[s] set <=> diagonal d has an entry among rows [32 s, 32 s + 32); filled only
+  // when skipping empty slices saves at least a tenth of the matrix bytes, else empty
+  std::vector<unsigned short> mask;
 };
 constexpr int kMaxDiag = 16;
 Dia build_dia(const Csc& M, const std::vector<int>* rows = nullptr);

@@ -40,6 +40,9 @@ struct DiaView {
   int off[kMaxDiagDev];  // ascending column offsets
   const double* val;     // val[d*ld + t], 0.0 = no entry
   const int* rows;       // row ids when the view is a subset, else nullptr
+  // optional: bit d of mask[t >> 5] is clear when diagonal d has no entry in the 32-row
+  // slice of row t, so the warp skips that 256-byte load (nullptr: all diagonals dense)
+  const unsigned short* mask;
 };
 
 // Compile-time bound on the number of diagonals, so the walk below is fully
@@ -54,10 +57,12 @@ template <int ND, class XLoad, class Fn>
 __device__ __forceinline__ void for_each_entry_x(const DiaViewT<ND>& S, int t, int row, XLoad&& xload, Fn&& fn) {
   const double* vp = S.val + t;
   double v[ND], xv[ND];
+  const unsigned m = S.mask ? S.mask[t >> 5] : 0xffffu;
 #pragma unroll
-  for (int d = 0; d < ND; ++d) v[d] = (d < S.n_diag) ? vp[(size_t)d * S.ld] : 0.0;
+  for (int d = 0; d < ND; ++d) v[d] = (d < S.n_diag && ((m >> d) & 1u)) ? vp[(size_t)d * S.ld] : 0.0;
 #pragma unroll
-  for (int d = 0; d < ND; ++d) xv[d] = (d < S.n_diag) ? xload(min(max(row + S.off[d], S.c_min), S.c_max)) : 0.0;
+  for (int d = 0; d < ND; ++d)
+    xv[d] = (d < S.n_diag && ((m >> d) & 1u)) ? xload(min(max(row + S.off[d], S.c_min), S.c_max)) : 0.0;
 #pragma unroll
   for (int d = 0; d < ND; ++d)
     if (v[d] != 0.0) fn(row + S.off[d], v[d], xv[d]);
@@ -507,6 +512,22 @@ __global__ void __launch_bounds__(256) k_restrict(const double* __restrict__ r, 
 // u[i] = u[i] + (P e)[i]; (P e)[2J+1] = 0 + 1 e[J]; (P e)[2J] = (0 + .5 e[J-1]) + .5 e[J]
 // with the terms whose coarse index is outside [0, n_coarse) absent
 // (interpolator.hpp:52-56,118-125; multigrid.hpp:294-296).
+// Two fine rows (an even row 2J and the odd row 2J+1) per thread: one 16-byte load / store of
+// u and the coarse entries e[J-1], e[J].  Needs fine_first even and u 16-byte aligned.
+__global__ void __launch_bounds__(256) k_prolong_add2(const double* __restrict__ e, int e_first, int n_coarse,
+                                                      double* __restrict__ u, int fine_first, int n_own) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+  const int t = 2 * p;
+  if (t >= n_own) return;
+  if (t + 1 < n_own) {
+    double2 v = *reinterpret_cast<double2*>(u + t);
+    v.x = __dadd_rn(v.x, prolong_at(e, e_first, n_coarse, fine_first + t));
+    v.y = __dadd_rn(v.y, prolong_at(e, e_first, n_coarse, fine_first + t + 1));
+    *reinterpret_cast<double2*>(u + t) = v;
+  } else {
+    u[t] = __dadd_rn(u[t], prolong_at(e, e_first, n_coarse, fine_first + t));
+  }
+}
 // u points at this rank's first owned fine row (global row fine_first), n_own rows.
 __global__ void __launch_bounds__(256) k_prolong_add(const double* __restrict__ e, int e_first, int n_coarse,
                                                      double* __restrict__ u, int fine_first, int n_own) {
@@ -530,12 +551,13 @@ struct HaloSide {
   unsigned long long* peer_flag;  // neighbour's flag for (site, the side I am on from its view)
   unsigned long long* my_flag;    // my flag the neighbour bumps
 };
-__global__ void __launch_bounds__(256) k_halo_exchange(HaloSide lo, HaloSide hi, unsigned long long* epoch,
+__global__ void __launch_bounds__(1024) k_halo_exchange(HaloSide lo, HaloSide hi, unsigned long long* epoch,
                                                        int* timed_out) {
   const HaloSide S = blockIdx.x == 0 ? lo : hi;
   if (S.peer_dst == nullptr) return;
   for (int i = threadIdx.x; i < S.count; i += blockDim.x) S.peer_dst[i] = S.src[i];
-  __threadfence_system();
+  // bar.sync orders every thread's peer stores before thread 0's release store below
+  // (release is cumulative over what happens-before it), so one system-scope release suffices
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long e = epoch[blockIdx.x] + 1;
@@ -550,7 +572,7 @@ __global__ void __launch_bounds__(256) k_halo_exchange(HaloSide lo, HaloSide hi,
         *timed_out = 1;
         break;
       }
-      __nanosleep(40);
+      __nanosleep(20);
     }
   }
   __syncthreads();
