@@ -230,7 +230,7 @@ struct Operator {
   // banded line-scan Gauss-Seidel (k_gs_rhs + k_gs_lines)
   bool lines_checked = false, lines_ok = false;
   dev::GsLineDesc line_desc[2];  // [0] forward, [1] backward
-  int lines_T = 0, lines_R = 0;  // threads; cp.async stages
+  int lines_T = 0, lines_R = 0, lines_rows = 1;  // threads; TMA stages; rows per thread
   size_t lines_smem = 0;
   // multicolour
   bool have_colors = false;
@@ -313,7 +313,8 @@ struct Operator {
     B = std::min(B, n);
     B &= ~1;  // even: every step's slice starts on a 16-byte boundary (TMA)
     if (B < 2) return;
-    lines_T = (B + 31) / 32 * 32;
+    lines_rows = B >= 256 ? 4 : 1;  // rows per thread
+    lines_T = ((B + lines_rows - 1) / lines_rows + 31) / 32 * 32;
     int ring = 64;
     while (ring < B + max_far + 1) ring <<= 1;
     const int n_far = (int)std::max(dists[0].size(), dists[1].size());
@@ -376,9 +377,15 @@ struct Operator {
     if (mode == AMGB_GS_AUTO && lines_ok && g_scratch) {
       const dev::GsLineDesc& L = line_desc[forward ? 0 : 1];
       with_view(colrows, [&](auto V) { launch_gs_rhs(V, L.dir, u, f, g_scratch, s); });
-      if (lines_R == 2) launch_gs_lines<2>(L, g_scratch, u, s);
-      else if (lines_R == 3) launch_gs_lines<3>(L, g_scratch, u, s);
-      else launch_gs_lines<4>(L, g_scratch, u, s);
+      if (lines_rows == 4) {
+        if (lines_R == 2) launch_gs_lines<2, 4>(L, g_scratch, u, s);
+        else if (lines_R == 3) launch_gs_lines<3, 4>(L, g_scratch, u, s);
+        else launch_gs_lines<4, 4>(L, g_scratch, u, s);
+      } else {
+        if (lines_R == 2) launch_gs_lines<2, 1>(L, g_scratch, u, s);
+        else if (lines_R == 3) launch_gs_lines<3, 1>(L, g_scratch, u, s);
+        else launch_gs_lines<4, 1>(L, g_scratch, u, s);
+      }
     } else {
       ensure_fronts(s);
       if (forward) gs_forward(f, u, s);
@@ -394,9 +401,9 @@ struct Operator {
   void launch_gs_rhs(SellView, int, const double*, const double*, double*, cudaStream_t) {
     throw ApiError(AMGB_ESTATE, "line-scan Gauss-Seidel needs the DIA layout");
   }
-  template <int STAGES>
+  template <int STAGES, int ROWS>
   void launch_gs_lines(const dev::GsLineDesc& L, const double* g, double* u, cudaStream_t s) {
-    auto kern = dev::k_gs_lines<STAGES>;
+    auto kern = dev::k_gs_lines<STAGES, ROWS>;
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

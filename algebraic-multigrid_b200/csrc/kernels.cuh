@@ -355,10 +355,13 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // One block, rows taken in sweep order in block steps of B.  Per step: the step's slices of
-// g / dinv / q / far coefficients arrive by TMA (issued STAGES-1 steps ahead by thread 0),
-// every thread forms c = g - sum far * u_new (ring), p = c * dinv, scans the affine maps
-// u_k = p_k + q_k u_{k-1}, and publishes u to the ring and to global memory.
-template <int STAGES>
+// g / dinv / q / far coefficients arrive by TMA (issued STAGES-1 steps ahead by thread 0);
+// every thread owns R consecutive rows of the block: it forms c = g - sum far * u_new (ring),
+// p = c * dinv, composes its R affine maps u_k = p_k + q_k u_{k-1}, the block scans the
+// per-thread maps, and each thread replays its rows from the value entering it and publishes
+// them to the ring and to global memory.  (R = 4: one warp scan per 128 rows -- the kernel is
+// instruction-issue bound on its single SM, and the scan is the largest share.)
+template <int STAGES, int R>
 __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* __restrict__ g, double* u) {
   extern __shared__ __align__(16) double smem[];
   double* ring = smem;                  // ring_mask + 1 doubles: most recent new values by position
@@ -395,47 +398,54 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
     for (int st = 0; st < STAGES - 1; ++st) issue(st);
 
   const int stage_stride = n_arr * B;
+  const int i0 = t * R;  // first row of this thread inside the block
   int sidx = 0, phase = 0;
   for (int step = 0; step < n_steps; ++step) {
     if (t == 0) issue(step + STAGES - 1);  // its buffer was released by the barrier ending step-1
     mbar_wait(&bars[sidx], (uint32_t)phase);
     const int b0 = step * B;
-    const int pos = b0 + t;
-    const bool ok = (t < B) && (pos < n);
-    Affine m{1.0, 0.0};  // identity for padding threads
-    bool keep = false;
-    if (ok) {
-      const double* src = stage + sidx * stage_stride + t;
-      double c = src[0];
-      const double dinv = src[B];
+    const double* src = stage + sidx * stage_stride + i0;
+    Affine rows[R];
+    Affine mine{1.0, 0.0};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < D.n_far) {
-          const double a = src[(3 + k) * B];
-          if (a != 0.0) c = __dsub_rn(c, __dmul_rn(a, ring[(pos - D.far_dist[k]) & D.ring_mask]));
+    for (int r = 0; r < R; ++r) {
+      const int pos = b0 + i0 + r;
+      Affine m{1.0, 0.0};  // identity for padding rows
+      if (i0 + r < B && pos < n) {
+        double c = src[r];
+        const double dinv = src[B + r];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < D.n_far) {
+            const double a = src[(3 + k) * B + r];
+            if (a != 0.0) c = __dsub_rn(c, __dmul_rn(a, ring[(pos - D.far_dist[k]) & D.ring_mask]));
+          }
+        }
+        m.p = c * dinv;
+        m.q = src[2 * B + r];
+        if (dinv == 0.0) {  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
+          m.p = u[D.dir > 0 ? pos : n - 1 - pos];
+          m.q = 0.0;
         }
       }
-      m.p = c * dinv;
-      m.q = src[2 * B];
-      keep = (dinv == 0.0);  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
-      if (keep) {
-        m.p = u[D.dir > 0 ? pos : n - 1 - pos];
-        m.q = 0.0;
-      }
+      rows[r] = m;
+      mine = compose(m, mine);
     }
     const double carry = (b0 > 0) ? ring[(b0 - 1) & D.ring_mask] : 0.0;
-    const Affine incl = warp_scan_affine(m, lane);
-    double x;
+    const Affine incl = warp_scan_affine(mine, lane);
+    // exclusive prefix inside the warp
+    Affine excl{__shfl_up_sync(0xffffffffu, incl.q, 1), __shfl_up_sync(0xffffffffu, incl.p, 1)};
+    if (lane == 0) excl = Affine{1.0, 0.0};
+    double in;  // value entering this warp
     if (n_warps == 1) {
-      x = incl.p + incl.q * carry;
+      in = carry;
       __syncwarp();
     } else if (D.short_carry) {
       // |q|^32 <= 2^-60: what enters a warp from further back than its predecessor is below
       // the last bit, so the value entering warp w is the predecessor's own last value
       if (lane == 31) wp[warp] = incl.p;
       __syncthreads();  // also: every ring read of this step happened before this point
-      const double in = (warp == 0) ? carry : wp[warp - 1];
-      x = incl.p + incl.q * in;
+      in = (warp == 0) ? carry : wp[warp - 1];
     } else {
       if (lane == 31) {
         wq[warp] = incl.q;
@@ -449,13 +459,17 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
         wp[lane] = w.p;
       }
       __syncthreads();
-      const Affine before = warp > 0 ? Affine{wq[warp - 1], wp[warp - 1]} : Affine{1.0, 0.0};
-      const Affine total = compose(incl, before);
-      x = total.p + total.q * carry;
+      in = (warp == 0) ? carry : wp[warp - 1] + wq[warp - 1] * carry;
     }
-    if (ok) {
-      ring[pos & D.ring_mask] = x;
-      u[D.dir > 0 ? pos : n - 1 - pos] = x;
+    double x = excl.p + excl.q * in;  // value entering this thread's first row
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pos = b0 + i0 + r;
+      if (i0 + r < B && pos < n) {
+        x = rows[r].p + rows[r].q * x;
+        ring[pos & D.ring_mask] = x;
+        u[D.dir > 0 ? pos : n - 1 - pos] = x;
+      }
     }
     __syncthreads();  // ring complete (and this step's stage buffer free) before the next step
     if (++sidx == STAGES) {
