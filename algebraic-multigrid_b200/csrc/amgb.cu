@@ -313,7 +313,7 @@ struct Operator {
     B = std::min(B, n);
     B &= ~1;  // even: every step's slice starts on a 16-byte boundary (TMA)
     if (B < 2) return;
-    lines_rows = B >= 256 ? 4 : 1;  // rows per thread
+    lines_rows = 1;  // rows per thread (4 measured slower: bank conflicts, profiles/r1_gs_linescan.md)
     lines_T = ((B + lines_rows - 1) / lines_rows + 31) / 32 * 32;
     int ring = 64;
     while (ring < B + max_far + 1) ring <<= 1;

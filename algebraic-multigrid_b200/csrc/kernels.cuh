@@ -399,10 +399,14 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
 
   const int stage_stride = n_arr * B;
   const int i0 = t * R;  // first row of this thread inside the block
+  // u is walked forwards or backwards in memory; pos = b0 + i0 + r
+  double* const u0 = (D.dir > 0) ? u + i0 : u + (n - 1 - i0);
+  const int ustep = (D.dir > 0) ? 1 : -1;
   int sidx = 0, phase = 0;
+  if (t == 0) mbar_wait(&bars[0], 0u);
+  __syncthreads();  // stage 0 has landed
   for (int step = 0; step < n_steps; ++step) {
     if (t == 0) issue(step + STAGES - 1);  // its buffer was released by the barrier ending step-1
-    mbar_wait(&bars[sidx], (uint32_t)phase);
     const int b0 = step * B;
     const double* src = stage + sidx * stage_stride + i0;
     Affine rows[R];
@@ -417,14 +421,14 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           if (k < D.n_far) {
-            const double a = src[(3 + k) * B + r];
-            if (a != 0.0) c = __dsub_rn(c, __dmul_rn(a, ring[(pos - D.far_dist[k]) & D.ring_mask]));
+            // absent entries are stored as 0 and the ring only ever holds finite values
+            c = __dsub_rn(c, __dmul_rn(src[(3 + k) * B + r], ring[(pos - D.far_dist[k]) & D.ring_mask]));
           }
         }
         m.p = c * dinv;
         m.q = src[2 * B + r];
         if (dinv == 0.0) {  // zero / absent diagonal: the reference leaves u unchanged (smoother.hpp:136)
-          m.p = u[D.dir > 0 ? pos : n - 1 - pos];
+          m.p = u0[(long long)ustep * (b0 + r)];
           m.q = 0.0;
         }
       }
@@ -468,14 +472,16 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
       if (i0 + r < B && pos < n) {
         x = rows[r].p + rows[r].q * x;
         ring[pos & D.ring_mask] = x;
-        u[D.dir > 0 ? pos : n - 1 - pos] = x;
+        u0[(long long)ustep * (b0 + r)] = x;
       }
     }
-    __syncthreads();  // ring complete (and this step's stage buffer free) before the next step
     if (++sidx == STAGES) {
       sidx = 0;
       phase ^= 1;
     }
+    // thread 0 makes sure the next step's stage has landed before everyone passes the barrier
+    if (t == 0 && step + 1 < n_steps) mbar_wait(&bars[sidx], (uint32_t)phase);
+    __syncthreads();  // ring complete, this step's stage buffer free, next stage visible
   }
 }
 
