@@ -377,6 +377,8 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
     for (int i = 0; i < STAGES; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // positions before the start of the sweep are read with a zero coefficient: keep them finite
+  for (int i = t; i <= D.ring_mask; i += T) ring[i] = 0.0;
   __syncthreads();
 
   auto issue = [&](int step) {  // thread 0 only
