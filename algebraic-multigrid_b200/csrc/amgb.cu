@@ -439,7 +439,27 @@ struct Operator {
     with_view(rows_of_A(), [&](auto V) {
       auto kern = dev::k_jacobi<decltype(V)>;
       V.n_rows = n;
-      LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, omega, out);
+      LAUNCH(kern, blocks_for(n, 256), 256, 0, s, V, u, f, omega, out, 0, n, 0);
+    });
+  }
+  // rows [begin, end) only
+  void jacobi_rows(const double* u, const double* f, double omega, double* out, int begin, int end,
+                   cudaStream_t s) const {
+    if (end <= begin) return;
+    with_view(rows_of_A(), [&](auto V) {
+      auto kern = dev::k_jacobi<decltype(V)>;
+      V.n_rows = end;
+      LAUNCH(kern, blocks_for(end - begin, 256), 256, 0, s, V, u, f, omega, out, begin, end, 0);
+    });
+  }
+  // rows [0, lo) and [n - hi, n) in one launch
+  void jacobi_edges(const double* u, const double* f, double omega, double* out, int lo, int hi,
+                    cudaStream_t s) const {
+    if (lo + hi <= 0) return;
+    with_view(rows_of_A(), [&](auto V) {
+      auto kern = dev::k_jacobi<decltype(V)>;
+      V.n_rows = n;
+      LAUNCH(kern, blocks_for(lo + hi, 256), 256, 0, s, V, u, f, omega, out, 0, lo, n - lo - hi);
     });
   }
   // first sweep from u = 0: only f and the diagonal are read (DIA); other layouts run the
@@ -618,16 +638,28 @@ struct amgb_hierarchy {
   DevBuf<int> timed_out;
   int n_sites = 0, site_cursor = 0;
   static constexpr int kMaxSites = 4096;
+  // second stream: the halo exchange of a sweep runs beside the sweep of the block interior
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;
 
   ~amgb_hierarchy() {
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (aux_stream) cudaStreamDestroy(aux_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
   // Map the neighbours' level vectors and flag arrays into this process.
   void setup_p2p() {
     if (!comm || world() < 2 || n_sharded == 0) return;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    const char* ov = std::getenv("AMGB_OVERLAP");
+    overlap = !(ov && std::string(ov) == "0");
     const char* env = std::getenv("AMGB_HALO");
     if (env && std::string(env) == "nccl") return;
     const int G = world(), g = rank();
@@ -812,8 +844,19 @@ struct amgb_hierarchy {
       }
       if (!done) {
         if (it == 0 && with_prolong) prolong_add(l, s);
-        exchange(l, src, s);
-        A.jacobi(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, s);
+        const int w = S.halo_lo;  // >= half-bandwidth: rows [w, n_own - w) read no halo entry
+        if (S.sharded && overlap && aux_stream && S.n_own > 4 * w) {
+          CUDA_CHECK(cudaEventRecord(ev_fork, s));
+          CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+          exchange(l, src, aux_stream);
+          A.jacobi_rows(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, w, S.n_own - w, s);
+          CUDA_CHECK(cudaEventRecord(ev_join, aux_stream));
+          CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
+          A.jacobi_edges(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, w, w, s);
+        } else {
+          exchange(l, src, s);
+          A.jacobi(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, s);
+        }
       }
       std::swap(src, dst);
     }

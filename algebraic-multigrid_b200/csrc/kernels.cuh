@@ -183,11 +183,16 @@ __global__ void __launch_bounds__(256) k_residual(M A, const double* __restrict_
 
 // ------------------------------------------------------------------ damped Jacobi
 // u_new[k] = u[k] + omega * (r_k / a_kk), r_k as in k_residual.
+// Rows row0 .. (skipping [hole_begin, hole_begin + hole_len)) up to A.n_rows: the sharded
+// V-cycle sweeps the interior of a row block while the halo exchange is in flight and the
+// rows next to the block edges afterwards (one launch with a hole in the middle).
 template <class M>
 __global__ void __launch_bounds__(256) k_jacobi(M A, const double* __restrict__ u,
                                                 const double* __restrict__ f, double omega,
-                                                double* __restrict__ u_new) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+                                                double* __restrict__ u_new, int row0, int hole_begin,
+                                                int hole_len) {
+  int t = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= hole_begin) t += hole_len;
   if (t >= A.n_rows) return;
   double acc = f[t], diag = 0.0;
   for_each_entry(A, t, t, u, [&](int c, double a, double xv) {
