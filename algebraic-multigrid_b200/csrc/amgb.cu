@@ -655,7 +655,11 @@ struct amgb_hierarchy {
   // Map the neighbours' level vectors and flag arrays into this process.
   void setup_p2p() {
     if (!comm || world() < 2 || n_sharded == 0) return;
-    CUDA_CHECK(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+    // highest priority: the two-block exchange kernel must be dispatched ahead of the
+    // thousands of blocks of the interior sweep it overlaps with
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, prio_hi));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     const char* ov = std::getenv("AMGB_OVERLAP");
@@ -848,7 +852,7 @@ struct amgb_hierarchy {
         if (S.sharded && overlap && aux_stream && S.n_own > 4 * w) {
           CUDA_CHECK(cudaEventRecord(ev_fork, s));
           CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
-          exchange(l, src, aux_stream);
+          exchange(l, src, aux_stream);  // enqueued first, on the high-priority stream
           A.jacobi_rows(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, w, S.n_own - w, s);
           CUDA_CHECK(cudaEventRecord(ev_join, aux_stream));
           CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
