@@ -718,32 +718,50 @@ __global__ void __launch_bounds__(32) k_banded_ldlt_solve_warp(const double* __r
     Lp = sL;
   }
   __syncwarp();
+  // the right-hand side is staged in shared memory once; factor entries and the element
+  // entering the window are fetched one pivot ahead of the dependent shuffle chain
+  for (int i = lane; i < n; i += 32) y[i] = f[i];
+  __syncwarp();
   // forward: window lane j = partial x[i + j]
-  double w = (lane < n) ? f[lane] : 0.0;
-  for (int i = 0; i < n; ++i) {
+  double w = (lane < n) ? y[lane] : 0.0;
+  auto fwd_l = [&](int i) {
     const int r = i + lane;
-    const double lij = (lane >= 1 && lane <= bw && r < n) ? Lp[(size_t)r * ld + (bw - lane)] : 0.0;
-    const double enter = (i + 32 < n) ? f[i + 32] : 0.0;
+    return (lane >= 1 && lane <= bw && r < n) ? Lp[(size_t)r * ld + (bw - lane)] : 0.0;
+  };
+  double lij = fwd_l(0);
+  double enter = (32 < n) ? y[32] : 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double l_next = fwd_l(i + 1);
+    const double e_next = (i + 33 < n) ? y[i + 33] : 0.0;
     const double xi = __shfl_sync(0xffffffffu, w, 0);
-    if (lane == 0) y[i] = xi;
-    if (lane >= 1 && lane <= bw && r < n) w = __dsub_rn(w, __dmul_rn(lij, xi));
+    if (lane == 0) y[i] = xi;  // rows <= i are final; the window has already consumed y[i]
+    if (lij != 0.0) w = __dsub_rn(w, __dmul_rn(lij, xi));
     w = __shfl_down_sync(0xffffffffu, w, 1);
     if (lane == 31) w = enter;
+    lij = l_next;
+    enter = e_next;
   }
   __syncwarp();
   for (int i = lane; i < n; i += 32) y[i] = __ddiv_rn(y[i], d[i]);
   __syncwarp();
   // backward: window lane j = partial z[i - j]
   w = (n - 1 - lane >= 0) ? y[n - 1 - lane] : 0.0;
-  for (int i = n - 1; i >= 0; --i) {
+  auto bwd_l = [&](int i) {
     const int c = i - lane;
-    const double lic = (lane >= 1 && lane <= bw && c >= 0) ? Lp[(size_t)i * ld + (bw - lane)] : 0.0;
-    const double enter = (i - 32 >= 0) ? y[i - 32] : 0.0;
+    return (i >= 0 && lane >= 1 && lane <= bw && c >= 0) ? Lp[(size_t)i * ld + (bw - lane)] : 0.0;
+  };
+  double lic = bwd_l(n - 1);
+  enter = (n - 33 >= 0) ? y[n - 33] : 0.0;
+  for (int i = n - 1; i >= 0; --i) {
+    const double l_next = bwd_l(i - 1);
+    const double e_next = (i - 33 >= 0) ? y[i - 33] : 0.0;
     const double xi = __shfl_sync(0xffffffffu, w, 0);
     if (lane == 0) x_out[i] = xi;
-    if (lane >= 1 && lane <= bw && c >= 0) w = __dsub_rn(w, __dmul_rn(lic, xi));
+    if (lic != 0.0) w = __dsub_rn(w, __dmul_rn(lic, xi));
     w = __shfl_down_sync(0xffffffffu, w, 1);
     if (lane == 31) w = enter;
+    lic = l_next;
+    enter = e_next;
   }
 }
 
