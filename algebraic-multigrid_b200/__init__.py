@@ -116,6 +116,8 @@ SIGNATURES = {
     "amgb_coarse_solve": (_i, [_p]),
     "amgb_kernel_launches": (_l, []),
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
+    "amgb_hierarchy_fused_legs": (_i, [_p, _i]),
+    "amgb_hierarchy_leg_plan": (_i, [_p, _i, _i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "amgb_hierarchy_pass_bytes": (_l, [_p, _i]),
     "amgb_hierarchy_vcycle_bytes": (_l, [_p]),
     "amgb_hierarchy_format": (_i, [_p, _i]),
@@ -390,7 +392,7 @@ class Multigrid:
 
     def __init__(self, interpolator, smoother, A, b, n_levels, tolerance=1e-9,
                  compute_error_every_n_iters=10, n_iters=100, use_graph=True,
-                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18, fuse=1):
+                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18, fuse=None):
         self.interpolator, self.smoother = interpolator, smoother
         o = Options()
         lib().amgb_options_default(C.byref(o))
@@ -404,7 +406,8 @@ class Multigrid:
         o.gs_mode = getattr(smoother, "mode", GS_AUTO)
         o.use_graph = int(use_graph)
         o.skip_dead_coarse_smooth = int(skip_dead_coarse_smooth)
-        o.fuse = int(fuse)
+        if fuse is not None:
+            o.fuse = int(fuse)
         b = _f64(b)
         h = _p()
         if comm is None:
@@ -582,6 +585,16 @@ class Multigrid:
 
     def launches_per_vcycle(self):
         return lib().amgb_hierarchy_launches_per_vcycle(self.h)
+
+    def fused_legs(self, level):
+        """True when `level` runs as one fused kernel per leg (option fuse bit 2)."""
+        return bool(lib().amgb_hierarchy_fused_legs(self.h, level))
+
+    def leg_plan(self, level, up=False):
+        info = np.zeros(10, np.int64)
+        _check(lib().amgb_hierarchy_leg_plan(self.h, level, int(up), info))
+        keys = ("m", "rho", "W", "LJ", "tiles", "strips", "PF", "threads", "smem_bytes", "NS")
+        return dict(zip(keys, info.tolist()))
 
     def time_kernel(self, level, kind, warmup=3, reps=10):
         ms = _d()

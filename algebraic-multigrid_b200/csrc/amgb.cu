@@ -17,7 +17,9 @@
 #include <cuda_runtime.h>
 
 #include "host_setup.hpp"
+#include "fused_leg.cuh"
 #include "kernels.cuh"
+#include "stream_leg.cuh"
 #include "nccl_dyn.hpp"
 
 namespace {
@@ -549,7 +551,7 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
-  o->fuse = 1;  // zero-guess sweep on; prolongation fusion (bit 1) measured slower
+  o->fuse = 1 | 4;  // zero-guess sweep and streaming legs on; prolongation fusion (bit 1) measured slower
 }
 
 }  // namespace
@@ -933,19 +935,203 @@ struct amgb_hierarchy {
   }
   std::vector<int64_t> coarse_block_start;  // block starts of level n_sharded (image of the fine blocks)
 
+  // ---- fused legs (fused_leg.cuh): one kernel per level and leg of the damped-Jacobi cycle
+  struct LegLevel {
+    bool ok = false;
+    bool stream = false;      // true: stream_leg.cuh (registers + shuffles); false: fused_leg.cuh (TMA rings)
+    leg::Plan down, up;
+    sleg::Params sdown{}, sup{};
+    unsigned mask = 0;
+    int kind_down = 0;
+  };
+  std::vector<LegLevel> legs;
+  static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+  }
+  template <int ND, int NS>
+  static void leg_attr() {
+    CUDA_CHECK(cudaFuncSetAttribute(leg::k_fused_leg<ND, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(leg::k_fused_leg<ND, NS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+  }
+  template <int ND, int NS>
+  static void leg_launch(const leg::Plan& pl, cudaStream_t s) {
+    auto kern = leg::k_fused_leg<ND, NS>;
+    LAUNCH(kern, pl.tiles, pl.threads, pl.smem_bytes, s, pl.P);
+  }
+  // action 0: opt the instantiation in to large dynamic shared memory; 1: launch
+  static void leg_dispatch(const leg::Plan& pl, int action, cudaStream_t s) {
+    auto go = [&](auto nd_tag) {
+      constexpr int ND = decltype(nd_tag)::value;
+      switch (pl.P.NS) {
+        case 1: action ? leg_launch<ND, 1>(pl, s) : leg_attr<ND, 1>(); break;
+        case 2: action ? leg_launch<ND, 2>(pl, s) : leg_attr<ND, 2>(); break;
+        case 3: action ? leg_launch<ND, 3>(pl, s) : leg_attr<ND, 3>(); break;
+        default: throw ApiError(AMGB_ESTATE, "fused leg: unsupported stage count");
+      }
+    };
+    if (pl.P.nd <= 6) go(std::integral_constant<int, 6>());
+    else go(std::integral_constant<int, 10>());
+  }
+  // ---- register-streaming legs (stream_leg.cuh)
+  template <int KIND, unsigned MASK>
+  static void sleg_launch(const sleg::Params& P, cudaStream_t s) {
+    auto kern = sleg::k_stream_leg<KIND, MASK, 2>;
+    LAUNCH(kern, (P.n_warps + 3) / 4, 128, 0, s, P);
+  }
+  template <int KIND>
+  static bool sleg_dispatch_mask(unsigned mask, const sleg::Params& P, cudaStream_t s, bool launch) {
+    switch (mask) {
+      case sleg::kMask5: if (launch) sleg_launch<KIND, sleg::kMask5>(P, s); return true;
+      case sleg::kMask7a: if (launch) sleg_launch<KIND, sleg::kMask7a>(P, s); return true;
+      case sleg::kMask7b: if (launch) sleg_launch<KIND, sleg::kMask7b>(P, s); return true;
+      case sleg::kMask9: if (launch) sleg_launch<KIND, sleg::kMask9>(P, s); return true;
+      default: return false;
+    }
+  }
+  // launch == false: only report whether the (kind, mask) pair has a kernel
+  static bool sleg_dispatch(int kind, unsigned mask, const sleg::Params& P, cudaStream_t s, bool launch) {
+    switch (kind) {
+      case sleg::DOWN_U: return sleg_dispatch_mask<sleg::DOWN_U>(mask, P, s, launch);
+      case sleg::DOWN_ZERO: return sleg_dispatch_mask<sleg::DOWN_ZERO>(mask, P, s, launch);
+      default: return sleg_dispatch_mask<sleg::UP>(mask, P, s, launch);
+    }
+  }
+  void leg_down(int l, cudaStream_t s) {
+    const LegLevel& G = legs[l];
+    if (G.stream) sleg_dispatch(G.kind_down, G.mask, G.sdown, s, true);
+    else leg_dispatch(G.down, 1, s);
+  }
+  void leg_up(int l, cudaStream_t s) {
+    const LegLevel& G = legs[l];
+    if (G.stream) sleg_dispatch(sleg::UP, G.mask, G.sup, s, true);
+    else leg_dispatch(G.up, 1, s);
+  }
+  // Plan the fused legs of level l (whole levels of a damped-Jacobi cycle with a banded DIA
+  // operator); levels the plan does not cover keep the per-operator kernels.
+  //   fuse bit 2: register-streaming legs for 3 x 3 line stencils (two sweeps per smooth call)
+  //   fuse bit 3: TMA-ring legs for the other banded levels
+  void prepare_legs(int l) {
+    if ((int)legs.size() != L) legs.assign(L, LegLevel());
+    LegLevel& G = legs[l];
+    G.ok = false;
+    if (!(opt.fuse & 12) || opt.smoother != AMGB_SMOOTHER_JACOBI || opt.smoother_iters < 1 || l + 1 >= L) return;
+    const LevelState& S = lv[l];
+    if (S.sharded || !S.tmp.p) return;
+    const DevMat& A = ops[l]->rows_of_A();
+    if (!A.is_dia || A.dia.n_diag > 10 || A.dia.rows.p) return;
+    const int kind_down = (l == 0) ? leg::DOWN_U : leg::DOWN_ZERO;
+    const int nu = (int)opt.smoother_iters;
+    G.kind_down = kind_down;
+    if ((opt.fuse & 4) && nu == 2) {
+      // line structure from the TMA-ring planner; the streaming kernels need rho == 1
+      leg::Plan st = leg::plan_leg(leg::UP, nu, (int)n[l], A.dia.n_diag, A.dia.off, 148, 200 * 1024);
+      if (st.ok && st.P.m < st.P.n && st.P.rho == 1) {
+        unsigned mask = 0;
+        for (int d = 0; d < A.dia.n_diag; ++d) mask |= 1u << ((st.P.line_a[d] + 1) * 3 + st.P.delta[d] + 1);
+        sleg::Params dummy{};
+        if (sleg_dispatch(kind_down, mask, dummy, nullptr, false) && sleg_dispatch(sleg::UP, mask, dummy, nullptr, false)) {
+          int n_sm = 148;
+          CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+          const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", A.dia.n_diag <= 5 ? 16 : 12);
+          auto plan = [&](int NS, int X) {
+            sleg::Params P{};
+            P.n = (int)n[l];
+            P.m = st.P.m;
+            P.n_lines = st.P.n_lines;
+            P.Wu = 32 - 2 * (NS + X);
+            P.n_strips = (P.m + P.Wu - 1) / P.Wu;
+            const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / 8));
+            P.LJ = (P.n_lines + chunks - 1) / chunks;
+            P.n_chunks = (P.n_lines + P.LJ - 1) / P.LJ;
+            P.n_warps = P.n_strips * P.n_chunks;
+            P.ld = A.dia.ld;
+            P.n_coarse = (int)n[l + 1];
+            P.omega = opt.omega;
+            P.val = A.dia.val.p;
+            P.f = S.f.p;
+            return P;
+          };
+          G.sdown = plan(kind_down == leg::DOWN_U ? nu + 1 : nu, 1);
+          G.sdown.uin = S.u.p;
+          G.sdown.uout = S.tmp.p;
+          G.sdown.fc = lv[l + 1].f.p;
+          G.sup = plan(nu, 0);
+          G.sup.uin = S.tmp.p;
+          G.sup.e = lv[l + 1].u.p;
+          G.sup.uout = S.u.p;
+          G.mask = mask;
+          G.stream = true;
+          G.ok = true;
+          return;
+        }
+      }
+    }
+    if (!(opt.fuse & 8)) return;
+    if ((kind_down == leg::DOWN_U ? nu + 1 : nu) > 3 || nu > 3) return;
+    int n_sm = 148;
+    CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    const int W_ovr = env_int("AMGB_LEG_W", 0), LJ_ovr = env_int("AMGB_LEG_LJ", 0), PF_ovr = env_int("AMGB_LEG_PF", 0);
+    const int occ_want = env_int("AMGB_LEG_OCC", 2);
+    auto plan = [&](int kind) {
+      leg::Plan pl;
+      for (int occ = occ_want; occ >= 1; --occ) {
+        const size_t cap = (size_t)(227 * 1024) / occ - (occ > 1 ? 1024 : 0);
+        pl = leg::plan_leg(kind, nu, (int)n[l], A.dia.n_diag, A.dia.off, n_sm * occ, cap, W_ovr, LJ_ovr, PF_ovr);
+        if (pl.ok && (occ == 1 || pl.P.W >= std::min(pl.P.m, 6 * pl.P.H))) break;
+      }
+      return pl;
+    };
+    G.down = plan(kind_down);
+    G.up = plan(leg::UP);
+    if (!G.down.ok || !G.up.ok) return;
+    auto fill = [&](leg::Plan& pl) {
+      pl.P.ld = A.dia.ld;
+      pl.P.val = A.dia.val.p;
+      pl.P.f = S.f.p;
+      pl.P.omega = opt.omega;
+      pl.P.n_coarse = (int)n[l + 1];
+    };
+    fill(G.down);
+    G.down.P.uin = S.u.p;
+    G.down.P.e = nullptr;
+    G.down.P.uout = S.tmp.p;
+    G.down.P.fc = lv[l + 1].f.p;
+    fill(G.up);
+    G.up.P.uin = S.tmp.p;
+    G.up.P.e = lv[l + 1].u.p;
+    G.up.P.uout = S.u.p;
+    G.up.P.fc = nullptr;
+    leg_dispatch(G.down, 0, nullptr);
+    leg_dispatch(G.up, 0, nullptr);
+    G.ok = true;
+  }
+  bool leg_ok(int l) const { return l >= 0 && l < (int)legs.size() && legs[l].ok; }
+
   void enqueue_vcycle(cudaStream_t s) {
     halo_exchanges_per_vcycle = 0;
     site_cursor = 0;  // sites 0 .. k-1 belong to the V-cycle, in the same order on every rank
     for (int l = 0; l < L; ++l) {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
+      if (leg_ok(l)) {  // sweeps + residual + restriction in one pass: u_l -> tmp_l, f_{l+1}
+        leg_down(l, s);
+        continue;
+      }
+      // a fused finer level does not zero u_l (its own coarse levels never read it)
+      if (l > 0 && leg_ok(l - 1)) CUDA_CHECK(cudaMemsetAsync(lv[l].u.p, 0, sizeof(double) * lv[l].u.n, s));
       smooth(l, s, /*from_zero=*/l > 0);
       if (!coarsest) residual_restrict(l, s);
       // on the coarsest level the reference also forms the residual (:272-274);
       // it is stored in a private member without a getter and never read.
     }
     coarse_solve(s);
-    for (int l = L - 2; l >= 0; --l) smooth(l, s, false, /*with_prolong=*/true);
+    for (int l = L - 2; l >= 0; --l) {
+      if (leg_ok(l)) leg_up(l, s);  // tmp_l + P u_{l+1}, sweeps -> u_l
+      else smooth(l, s, false, /*with_prolong=*/true);
+    }
   }
   void build_graph() {
     if (exec) return;
@@ -1361,16 +1547,18 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
       S.n_own = S.n_mat = (int)h->n[l];
       h->ops[l]->build(std::move(mats[l]), s);
     }
-    S.u.alloc(S.n_vec());
+    // +8: the fused legs copy 16-byte aligned windows, which may reach one entry past the end
+    S.u.alloc(S.n_vec() + 8);
     S.u.zero(s);
-    S.f.alloc(S.n_mat);
+    S.f.alloc(S.n_mat + 8);
     S.f.zero(s);
     if (o.smoother == AMGB_SMOOTHER_JACOBI) {
-      S.tmp.alloc(S.n_vec());
+      S.tmp.alloc(S.n_vec() + 8);
       S.tmp.zero(s);
     }
     if (!(l + 1 == L && o.skip_dead_coarse_smooth)) h->prepare_smoother(l);
   }
+  for (int l = 0; l < L; ++l) h->prepare_legs(l);
   h->upload_f(0, b);
   h->partial.alloc(std::max(1, blocks_for(h->lv[0].n_own, 256)));
   h->scalar.alloc(1);
@@ -1715,6 +1903,42 @@ int amgb_coarse_solve(amgb_hierarchy* h) {
   });
 }
 
+int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level) {
+  return (h && h->leg_ok(level)) ? 1 : 0;
+}
+int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info) {
+  return guarded([&] {
+    if (!h || !info) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    if (!h->leg_ok(level)) throw ApiError(AMGB_ESTATE, "level has no fused legs");
+    if (h->legs[level].stream) {
+      const sleg::Params& P = up ? h->legs[level].sup : h->legs[level].sdown;
+      info[0] = P.m;
+      info[1] = 1;
+      info[2] = P.Wu;
+      info[3] = P.LJ;
+      info[4] = (P.n_warps + 3) / 4;
+      info[5] = P.n_strips;
+      info[6] = 2;
+      info[7] = 128;
+      info[8] = 0;
+      info[9] = (32 - P.Wu) / 2 - (up ? 0 : 1);
+      return;
+    }
+    const leg::Plan& pl = up ? h->legs[level].up : h->legs[level].down;
+    info[0] = pl.P.m;
+    info[1] = pl.P.rho;
+    info[2] = pl.P.W;
+    info[3] = pl.P.LJ;
+    info[4] = pl.tiles;
+    info[5] = pl.P.n_strips;
+    info[6] = pl.P.PF;
+    info[7] = pl.threads;
+    info[8] = (int64_t)pl.smem_bytes;
+    info[9] = pl.P.NS;
+  });
+}
+
 int64_t amgb_kernel_launches(void) { return g_launches.load(); }
 int64_t amgb_hierarchy_launches_per_vcycle(const amgb_hierarchy* h) {
   return h ? h->launches_per_vcycle : 0;
@@ -1752,6 +1976,40 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
     if (!h || !ms_out || reps < 1) throw std::invalid_argument("bad argument");
     h->check_level(level, kind >= 2);
     if (kind >= 2) h->require_whole(level);
+    if (kind == 4 || kind == 5) {
+      // fused down / up leg of this level; they work on the level state, which is restored
+      if (!h->leg_ok(level)) throw ApiError(AMGB_ESTATE, "level has no fused legs");
+      CUDA_CHECK(cudaSetDevice(h->device));
+      cudaStream_t s = h->stream;
+      LevelState& S = h->lv[level];
+      LevelState& C = h->lv[level + 1];
+      DevBuf<double> su, sf;
+      su.alloc(S.u.n);
+      sf.alloc(C.f.n);
+      CUDA_CHECK(cudaMemcpyAsync(su.p, S.u.p, sizeof(double) * S.u.n, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(sf.p, C.f.p, sizeof(double) * C.f.n, cudaMemcpyDeviceToDevice, s));
+      auto once = [&] {
+        if (kind == 4) h->leg_down(level, s);
+        else h->leg_up(level, s);
+      };
+      for (int i = 0; i < warmup; ++i) once();
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, s));
+      for (int i = 0; i < reps; ++i) once();
+      CUDA_CHECK(cudaEventRecord(e1, s));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      CUDA_CHECK(cudaMemcpyAsync(S.u.p, su.p, sizeof(double) * S.u.n, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemcpyAsync(C.f.p, sf.p, sizeof(double) * C.f.n, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      *ms_out = (double)ms / reps;
+      return;
+    }
     CUDA_CHECK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     h->prepare_smoother(level);

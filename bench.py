@@ -262,32 +262,57 @@ def run_b200(a):
     # index array; SELL: 12 B per stored entry) + f read + u read + result write (24 N).
     # The CSR-based figure of SURVEY.md 8(d) (12 nnz + 28 N + 4) is reported beside it.
     peak, peak_src = measured_hbm_peak()
-    kern_ms = mg.time_kernel(0, 0, warmup=3, reps=20)
     n1 = mg.get_n_dofs(1)
     r0, r1 = mg.local_range(0)
-    bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0)       # this rank's row block
     survey0 = mg.pass_bytes(0)
+    fused0 = world == 1 and mg.fused_legs(0)
+    per_kernel = {}
+    if fused0:
+        # fused down leg of level 0 (sweeps + residual + restriction in one pass): operator,
+        # f and u read once, smoothed u written once, coarse rhs written once
+        kern_ms = mg.time_kernel(0, 4, warmup=3, reps=20)
+        bytes0 = mg.matrix_bytes(0) + 24 * N0 + 8 * n1
+        plan = mg.leg_plan(0)
+        kname = "k_stream_leg" if plan["smem_bytes"] == 0 else "k_fused_leg"
+        kdesc = "%s down leg (level 0: %d Jacobi sweeps + residual + restriction in one pass, %s layout)" % (
+            kname, smoother.n_iters, mg.format(0))
+    else:
+        kern_ms = mg.time_kernel(0, 0, warmup=3, reps=20)
+        bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0)       # this rank's row block
+        plan = None
+        kname = {"jacobi": "k_jacobi", "color": "k_color_gs", "gs": "k_gs_fronts"}[a.smoother]
+        kdesc = kname + " (level 0, %s layout)" % mg.format(0)
     achieved = bytes0 / (kern_ms * 1e-3) / 1e9
-    kname = {"jacobi": "k_jacobi", "color": "k_color_gs", "gs": "k_gs_fronts"}[a.smoother]
-    roofline = {"bound": "hbm", "kernel": kname + " (level 0, %s layout)" % mg.format(0),
+    roofline = {"bound": "hbm", "kernel": kdesc,
                 "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes0, "ms_per_launch": kern_ms,
                 "survey_formula_bytes_per_launch": survey0,
                 "survey_formula_GBps": survey0 / (kern_ms * 1e-3) / 1e9,
                 "traffic": ncu_traffic(kname)}
-    per_kernel = {}
-    for kind, nm in ((1, "residual"), (2, "residual_restrict"), (3, "prolong_add")) if world == 1 else ():
+    if plan:
+        roofline["tiling"] = plan
+    pass0 = mg.matrix_bytes(0) + 24 * (r1 - r0)
+    kinds = [(0, "smoother_sweep"), (1, "residual"), (2, "residual_restrict"), (3, "prolong_add")]
+    if fused0:
+        kinds += [(4, "fused_down_leg"), (5, "fused_up_leg")]
+    for kind, nm in kinds if world == 1 else ():
         t_ms = mg.time_kernel(0, kind, warmup=3, reps=20)
-        alg = {1: bytes0, 2: mg.matrix_bytes(0) + 16 * N0 + 8 * n1, 3: 8 * n1 + 16 * N0}[kind]
+        alg = {0: pass0, 1: pass0, 2: mg.matrix_bytes(0) + 16 * N0 + 8 * n1, 3: 8 * n1 + 16 * N0,
+               4: mg.matrix_bytes(0) + 24 * N0 + 8 * n1, 5: mg.matrix_bytes(0) + 24 * N0 + 8 * n1}[kind]
         per_kernel[nm] = {"ms": t_ms, "GB/s": alg / (t_ms * 1e-3) / 1e9,
                           "frac": alg / (t_ms * 1e-3) / 1e9 / peak}
-    # bytes one V-cycle must move with the layouts in use
+    # bytes one V-cycle must move with the layouts and kernels in use
     passes = 2 * smoother.n_iters if a.smoother == "jacobi" else 4 * smoother.n_iters
     layout_bytes = 0
     for l in range(levels - 1):
         nl, nn = mg.get_n_dofs(l), mg.get_n_dofs(l + 1)
-        layout_bytes += (passes + 1) * (mg.matrix_bytes(l) + 24 * nl) + 24 * nl + 16 * nn
+        if world == 1 and mg.fused_legs(l):
+            down = mg.matrix_bytes(l) + (24 if l == 0 else 16) * nl + 8 * nn
+            up = mg.matrix_bytes(l) + 24 * nl + 8 * nn
+            layout_bytes += down + up
+        else:
+            layout_bytes += (passes + 1) * (mg.matrix_bytes(l) + 24 * nl) + 24 * nl + 16 * nn
     vbytes = mg.vcycle_bytes()
 
     if rank != 0:
@@ -325,6 +350,7 @@ def run_b200(a):
                                       mg.halo_exchanges_per_vcycle()),
                    "mdof_per_s": vps * N0 / 1e6, "setup_s": setup_s,
                    "rss_after_timed_cycles": rss_after,
+                   "fused_legs": [bool(world == 1 and mg.fused_legs(l)) for l in range(levels - 1)],
                    "vcycle_layout_bytes": layout_bytes,
                    "vcycle_hbm_frac": (layout_bytes / (ms / a.steps * 1e-3) / 1e9 / peak) if world == 1 else None,
                    "vcycle_survey_formula_bytes": vbytes,

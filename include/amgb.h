@@ -142,8 +142,12 @@ typedef struct amgb_options {
   int fuse;                 /* bit 0 (default on): damped-Jacobi cycles skip the operator read
                                of the first pre-smoothing sweep on coarse levels (u = 0
                                there); bit 1 (default off: measured slower, profiles/):
-                               fold u += P e into the first post-smoothing sweep.  The
-                               arithmetic, hence every bit of the result, is unchanged   */
+                               fold u += P e into the first post-smoothing sweep; bit 2
+                               (default on): fused legs -- per level ONE kernel for
+                               sweeps + residual + restriction (multigrid.hpp:268-282) and
+                               ONE for prolongation + add + sweeps (:294-301), each reading
+                               the operator from HBM once.  The arithmetic, hence every bit
+                               of the result, is unchanged                               */
 } amgb_options;
 void amgb_options_default(amgb_options* opt);
 
@@ -249,6 +253,14 @@ int amgb_residual_restrict_level(amgb_hierarchy* h, int level);
 /* coarsest direct solve u_L = A_L^{-1} f_L (multigrid.hpp:287-288) */
 int amgb_coarse_solve(amgb_hierarchy* h);
 
+/* 1 when `level` runs as fused legs (option fuse bit 2; whole banded levels of a damped-Jacobi
+ * cycle), else 0.  amgb_hierarchy_leg_plan reports the tiling of its down (up = 0) or up leg:
+ * info[0..9] = line length m, element halo per stage, strip width W, lines per tile, tiles
+ * (= CTAs), strips, TMA lines in flight, threads per CTA, dynamic shared memory bytes, chained
+ * stencil stages. */
+int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level);
+int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info);
+
 /* counters: kernels launched by this library in this process, and per V-cycle */
 int64_t amgb_kernel_launches(void);
 int64_t amgb_hierarchy_launches_per_vcycle(const amgb_hierarchy* h);
@@ -267,7 +279,8 @@ int64_t amgb_hierarchy_vcycle_bytes(const amgb_hierarchy* h);
 /* ------------------------------------------------------------------------
  * Per-kernel timing hooks for bench.py (CUDA events on the handle's stream).
  * kind: 0 smoother pass (one Jacobi sweep / one colour-complete pass / one GS
- * direction), 1 residual, 2 residual+restrict, 3 prolong+add.  Runs `reps`
+ * direction), 1 residual, 2 residual+restrict, 3 prolong+add, 4 fused down leg,
+ * 5 fused up leg (levels with amgb_hierarchy_fused_legs).  Runs `reps`
  * launches after `warmup`, returns the mean milliseconds per launch.
  * ---------------------------------------------------------------------- */
 int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int reps,

@@ -365,6 +365,52 @@ def test_fused_jacobi_cycle_is_bit_identical(n, L, eps):
     assert fused.launches_per_vcycle() < plain.launches_per_vcycle()
 
 
+@pytest.mark.parametrize("fuse", [5, 9, 13])
+@pytest.mark.parametrize("n,L,eps,nu", [(35, 8, 1.0, 2), (64, 6, 1.0, 2), (100, 9, 1.0, 2), (129, 10, 1e-3, 2),
+                                        (129, 12, 1.0, 1), (257, 13, 1.0, 2), (200, 11, 1.0, 3),
+                                        (513, 14, 1.0, 2)])
+def test_fused_legs_cycle_is_bit_identical(n, L, eps, nu, fuse):
+    """Fused legs (one kernel per level and leg, operator read once) against the per-operator
+    kernels and the oracle: every level's iterate and right-hand side, bit for bit.
+    fuse bit 2 = register-streaming legs (3 x 3 line stencils, two sweeps), bit 3 = TMA-ring legs."""
+    sm = amg.DampedJacobi(2.0 / 3.0, nu)
+    legs, mo, _ = make_pair(n, L, sm, eps, fuse=fuse)
+    plain, _, _ = make_pair(n, L, sm, eps, fuse=0)
+    n_fused = sum(legs.fused_legs(l) for l in range(L - 1))
+    if (fuse & 8) or (nu == 2 and n >= 100):
+        assert n_fused > 0
+    assert not any(plain.fused_legs(l) for l in range(L))
+    for _ in range(3):
+        legs.vcycle(); plain.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert legs.get_soln(l).tobytes() == plain.get_soln(l).tobytes(), l
+        assert legs.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert legs.get_rhs(l).tobytes() == mo.f(l).tobytes(), l
+    if n_fused:
+        assert legs.launches_per_vcycle() < plain.launches_per_vcycle()
+
+
+def test_fused_legs_small_tiles(monkeypatch):
+    """Force narrow strips / short line chunks so one level is cut into many tiles."""
+    monkeypatch.setenv("AMGB_LEG_W", "37")
+    monkeypatch.setenv("AMGB_LEG_LJ", "11")
+    sm = amg.DampedJacobi(2.0 / 3.0, 2)
+    legs, mo, _ = make_pair(257, 12, sm, 1.0, fuse=9)
+    assert legs.leg_plan(0)["W"] <= 37 and legs.leg_plan(0)["tiles"] > 100
+    for _ in range(2):
+        legs.vcycle(); mo.vcycle()
+    for l in range(12):
+        assert legs.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+
+
+def test_fused_legs_iteration_count_matches_oracle():
+    sm = amg.DampedJacobi(2.0 / 3.0, 2)
+    legs, mo, _ = make_pair(35, 8, sm, 1.0, every=5, n_iters=400, fuse=5)
+    legs.solve(); mo.solve()
+    assert legs.iters_done == mo.iters_done
+    np.testing.assert_allclose(legs.error_history(), mo.history(), rtol=1e-12)
+
+
 def test_relative_residual_criterion():
     mg, mo, _ = make_pair(35, 8, amg.SparseGaussSeidel(mode=amg.GS_LEVELSCHED), every=1, n_iters=200)
     A, b, Ao = problem(35)
