@@ -910,6 +910,22 @@ struct amgb_hierarchy {
     const size_t xbytes = sizeof(double) * (size_t)nc;
     const size_t lbytes = sizeof(double) * (size_t)nc * std::max(bw, 1);
     const size_t cap = 200 * 1024;
+    if (bw >= 1 && bw <= 8 && xbytes + lbytes <= 48 * 1024) {
+      const size_t smem = xbytes + lbytes;
+      double* fL = lv[L - 1].f.p;
+      double* uL = lv[L - 1].u.p;
+      switch (bw) {
+        case 1: LAUNCH(dev::k_banded_ldlt_solve_serial<1>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+        case 2: LAUNCH(dev::k_banded_ldlt_solve_serial<2>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+        case 3: LAUNCH(dev::k_banded_ldlt_solve_serial<3>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+        case 4: LAUNCH(dev::k_banded_ldlt_solve_serial<4>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+        case 5: LAUNCH(dev::k_banded_ldlt_solve_serial<5>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+        case 6: LAUNCH(dev::k_banded_ldlt_solve_serial<6>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+        case 7: LAUNCH(dev::k_banded_ldlt_solve_serial<7>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+        default: LAUNCH(dev::k_banded_ldlt_solve_serial<8>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
+      }
+      return;
+    }
     if (bw <= 31 && xbytes <= cap) {
       const int l_smem = xbytes + lbytes <= cap;
       const size_t smem = xbytes + (l_smem ? lbytes : 0);
@@ -976,37 +992,48 @@ struct amgb_hierarchy {
     else go(std::integral_constant<int, 10>());
   }
   // ---- register-streaming legs (stream_leg.cuh)
+  // action 0: does a kernel exist for (kind, mask)?  1: launch.  2: set the L1 carve-out (outside
+  // stream capture) and report the resident warps per SM the register count allows.
   template <int KIND, unsigned MASK>
-  static void sleg_launch(const sleg::Params& P, cudaStream_t s) {
+  static void sleg_do(const sleg::Params& P, cudaStream_t s, int action, int* warps_per_sm) {
     auto kern = sleg::k_stream_leg<KIND, MASK, 2>;
-    LAUNCH(kern, (P.n_warps + 3) / 4, 128, 0, s, P);
+    if (action == 1) {
+      LAUNCH(kern, (P.n_warps + 3) / 4, 128, 0, s, P);
+    } else if (action == 2) {
+      cudaFuncAttributes fa{};
+      CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
+      if (warps_per_sm) *warps_per_sm = std::max(1, 65536 / (std::max(fa.numRegs, 1) * 128)) * 4;
+      // no shared memory: leave the whole array to the L1 (neighbouring warps' halo columns hit there)
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxL1));
+    }
   }
   template <int KIND>
-  static bool sleg_dispatch_mask(unsigned mask, const sleg::Params& P, cudaStream_t s, bool launch) {
+  static bool sleg_dispatch_mask(unsigned mask, const sleg::Params& P, cudaStream_t s, int action, int* wps) {
     switch (mask) {
-      case sleg::kMask5: if (launch) sleg_launch<KIND, sleg::kMask5>(P, s); return true;
-      case sleg::kMask7a: if (launch) sleg_launch<KIND, sleg::kMask7a>(P, s); return true;
-      case sleg::kMask7b: if (launch) sleg_launch<KIND, sleg::kMask7b>(P, s); return true;
-      case sleg::kMask9: if (launch) sleg_launch<KIND, sleg::kMask9>(P, s); return true;
+      case sleg::kMask5: sleg_do<KIND, sleg::kMask5>(P, s, action, wps); return true;
+      case sleg::kMask7a: sleg_do<KIND, sleg::kMask7a>(P, s, action, wps); return true;
+      case sleg::kMask7b: sleg_do<KIND, sleg::kMask7b>(P, s, action, wps); return true;
+      case sleg::kMask9: sleg_do<KIND, sleg::kMask9>(P, s, action, wps); return true;
       default: return false;
     }
   }
-  // launch == false: only report whether the (kind, mask) pair has a kernel
-  static bool sleg_dispatch(int kind, unsigned mask, const sleg::Params& P, cudaStream_t s, bool launch) {
+  static bool sleg_dispatch(int kind, unsigned mask, const sleg::Params& P, cudaStream_t s, int action,
+                            int* wps = nullptr) {
     switch (kind) {
-      case sleg::DOWN_U: return sleg_dispatch_mask<sleg::DOWN_U>(mask, P, s, launch);
-      case sleg::DOWN_ZERO: return sleg_dispatch_mask<sleg::DOWN_ZERO>(mask, P, s, launch);
-      default: return sleg_dispatch_mask<sleg::UP>(mask, P, s, launch);
+      case sleg::DOWN_U: return sleg_dispatch_mask<sleg::DOWN_U>(mask, P, s, action, wps);
+      case sleg::DOWN_ZERO: return sleg_dispatch_mask<sleg::DOWN_ZERO>(mask, P, s, action, wps);
+      default: return sleg_dispatch_mask<sleg::UP>(mask, P, s, action, wps);
     }
   }
   void leg_down(int l, cudaStream_t s) {
     const LegLevel& G = legs[l];
-    if (G.stream) sleg_dispatch(G.kind_down, G.mask, G.sdown, s, true);
+    if (G.stream) sleg_dispatch(G.kind_down, G.mask, G.sdown, s, 1);
     else leg_dispatch(G.down, 1, s);
   }
   void leg_up(int l, cudaStream_t s) {
     const LegLevel& G = legs[l];
-    if (G.stream) sleg_dispatch(sleg::UP, G.mask, G.sup, s, true);
+    if (G.stream) sleg_dispatch(sleg::UP, G.mask, G.sup, s, 1);
     else leg_dispatch(G.up, 1, s);
   }
   // Plan the fused legs of level l (whole levels of a damped-Jacobi cycle with a banded DIA
@@ -1032,11 +1059,13 @@ struct amgb_hierarchy {
         unsigned mask = 0;
         for (int d = 0; d < A.dia.n_diag; ++d) mask |= 1u << ((st.P.line_a[d] + 1) * 3 + st.P.delta[d] + 1);
         sleg::Params dummy{};
-        if (sleg_dispatch(kind_down, mask, dummy, nullptr, false) && sleg_dispatch(sleg::UP, mask, dummy, nullptr, false)) {
+        if (sleg_dispatch(kind_down, mask, dummy, nullptr, 0) && sleg_dispatch(sleg::UP, mask, dummy, nullptr, 0)) {
           int n_sm = 148;
           CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-          const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", A.dia.n_diag <= 5 ? 16 : 12);
-          auto plan = [&](int NS, int X) {
+          auto plan = [&](int kind, int NS, int X) {
+            int wps = 12;
+            sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
+            const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", wps);
             sleg::Params P{};
             P.n = (int)n[l];
             P.m = st.P.m;
@@ -1054,11 +1083,11 @@ struct amgb_hierarchy {
             P.f = S.f.p;
             return P;
           };
-          G.sdown = plan(kind_down == leg::DOWN_U ? nu + 1 : nu, 1);
+          G.sdown = plan(kind_down, kind_down == leg::DOWN_U ? nu + 1 : nu, 1);
           G.sdown.uin = S.u.p;
           G.sdown.uout = S.tmp.p;
           G.sdown.fc = lv[l + 1].f.p;
-          G.sup = plan(nu, 0);
+          G.sup = plan(sleg::UP, nu, 0);
           G.sup.uin = S.tmp.p;
           G.sup.e = lv[l + 1].u.p;
           G.sup.uout = S.u.p;

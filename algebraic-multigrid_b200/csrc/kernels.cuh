@@ -765,5 +765,63 @@ __global__ void __launch_bounds__(32) k_banded_ldlt_solve_warp(const double* __r
   }
 }
 
+// Same solve for half-bandwidth BW <= 8 as a plain recurrence: one thread keeps the last BW
+// results in registers, so a row costs one short multiply-subtract chain (~20 cycles) instead
+// of the shuffle round trips of the warp kernel (~180 cycles per pivot).  Every entry receives
+// its updates in the order of k_banded_ldlt_solve (ascending pivot forward, descending pivot
+// backward), i.e. the oracle's order.  Factor, diagonal and vector are staged in shared memory
+// by the whole warp; the division pass is spread over the lanes.
+template <int BW>
+__global__ void __launch_bounds__(32) k_banded_ldlt_solve_serial(const double* __restrict__ L,
+                                                                 const double* __restrict__ d, int n,
+                                                                 const double* __restrict__ f,
+                                                                 double* __restrict__ x_out) {
+  extern __shared__ double sm[];
+  double* y = sm;               // n
+  double* sL = sm + n;          // n * BW
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n * BW; i += 32) sL[i] = L[i];
+  for (int i = lane; i < n; i += 32) y[i] = f[i];
+  __syncwarp();
+  if (lane == 0) {
+    double win[BW];  // win[t - 1] = y[r - t]
+#pragma unroll
+    for (int t = 0; t < BW; ++t) win[t] = 0.0;
+#pragma unroll 4
+    for (int r = 0; r < n; ++r) {
+      double acc = y[r];
+      const double* lr = sL + (size_t)r * BW;
+#pragma unroll
+      for (int t = BW; t >= 1; --t)
+        if (r - t >= 0) acc = __dsub_rn(acc, __dmul_rn(lr[BW - t], win[t - 1]));
+#pragma unroll
+      for (int t = BW - 1; t >= 1; --t) win[t] = win[t - 1];
+      win[0] = acc;
+      y[r] = acc;
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) y[i] = __ddiv_rn(y[i], d[i]);
+  __syncwarp();
+  if (lane == 0) {
+    double win[BW];  // win[t - 1] = x[c + t]
+#pragma unroll
+    for (int t = 0; t < BW; ++t) win[t] = 0.0;
+#pragma unroll 4
+    for (int c = n - 1; c >= 0; --c) {
+      double acc = y[c];
+#pragma unroll
+      for (int t = BW; t >= 1; --t)
+        if (c + t < n) acc = __dsub_rn(acc, __dmul_rn(sL[(size_t)(c + t) * BW + (BW - t)], win[t - 1]));
+#pragma unroll
+      for (int t = BW - 1; t >= 1; --t) win[t] = win[t - 1];
+      win[0] = acc;
+      y[c] = acc;
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) x_out[i] = y[i];
+}
+
 }  // namespace dev
 }  // namespace amgb

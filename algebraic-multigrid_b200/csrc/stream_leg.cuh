@@ -17,7 +17,11 @@
 // 32 - 2H middle lanes (H = stages [+ 1 for the restriction]) and neighbouring warps overlap.
 // The operator rows, f and the input of the line PF steps ahead are loaded straight into a
 // register ring (coalesced 256-byte requests per warp and array); the ring is indexed with
-// compile-time slots by unrolling the line loop over its period.
+// compile-time slots by unrolling the line loop over its period.  The kernels use no shared
+// memory and ask for the largest L1 carve-out: the halo columns neighbouring warps share are
+// served from L1.  (A variant that prefetched deeper through a per-warp cp.async FIFO in shared
+// memory measured slower at every level -- more load/store-unit work per row and a smaller L1;
+// profiles/r1_stream_legs.md.)
 //
 // Per-row arithmetic (operation order, no FMA contraction) is that of k_jacobi /
 // k_jacobi_zero / k_residual_restrict / k_prolong_add (kernels.cuh): bit-identical results.

@@ -248,6 +248,21 @@ def test_fused_residual_restrict_and_coarse_solve(n, L, eps):
     assert rel(dense @ mg.get_soln(L - 1), fL) <= 1e-10
 
 
+@pytest.mark.parametrize("n,L", [(35, 8), (35, 6), (35, 5), (35, 4), (35, 3), (64, 6), (64, 4), (129, 12),
+                                 (129, 9), (257, 13)])
+def test_coarse_solve_every_bandwidth(n, L):
+    """Coarsest direct solve (multigrid.hpp:287-288) for half-bandwidths 1..8 (serial-recurrence
+    kernel), 9..31 (warp kernel) and wider (block kernel): the oracle's banded LDL^T, bit for bit."""
+    mg, mo, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), 1.0)
+    N = mg.get_n_dofs(L - 1)
+    for seed in (3, 4):
+        fL = vec(N, seed)
+        mg.set_rhs(L - 1, fL)
+        mg.coarse_solve()
+        want = O.Ldlt(mo.A(L - 1)).solve(fL)
+        assert np.array_equal(mg.get_soln(L - 1), want)
+
+
 SMOOTHERS = [
     ("gs", lambda: amg.SparseGaussSeidel(mode=amg.GS_LEVELSCHED)),
     ("gs_linescan", lambda: amg.SparseGaussSeidel()),
