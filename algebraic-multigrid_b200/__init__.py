@@ -117,6 +117,7 @@ SIGNATURES = {
     "amgb_kernel_launches": (_l, []),
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
     "amgb_hierarchy_fused_legs": (_i, [_p, _i]),
+    "amgb_hierarchy_tail_first": (_i, [_p]),
     "amgb_hierarchy_leg_plan": (_i, [_p, _i, _i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "amgb_hierarchy_pass_bytes": (_l, [_p, _i]),
     "amgb_hierarchy_vcycle_bytes": (_l, [_p]),
@@ -589,6 +590,10 @@ class Multigrid:
     def fused_legs(self, level):
         """True when `level` runs as one fused kernel per leg (option fuse bit 2)."""
         return bool(lib().amgb_hierarchy_fused_legs(self.h, level))
+
+    def tail_first(self):
+        """First level of the coarse tail that runs in one launch (-1: none)."""
+        return lib().amgb_hierarchy_tail_first(self.h)
 
     def leg_plan(self, level, up=False):
         info = np.zeros(10, np.int64)

@@ -271,6 +271,29 @@ struct Operator {
     colrows.dia.c_min = -halo_lo;
     colrows.dia.c_max = n_own + halo_hi - 1;
   }
+  // Window mirror for the fused legs of a sharded level: rows [row_begin, row_begin + n_rows) of A
+  // (rows outside the level stay empty), diagonals ordered like the whole operator's.
+  DevDia win;
+  std::vector<int> win_off;
+  bool build_window(int row_begin, int n_rows, cudaStream_t s) {
+    const Csc& R = host_rows_of_A();
+    std::vector<int> offs;
+    for (int r = 0; r < R.cols; ++r)
+      for (int p = R.colptr[r]; p < R.colptr[r + 1]; ++p) {
+        if (R.val[p] == 0.0) continue;
+        const int o = R.rowidx[p] - r;
+        auto it = std::lower_bound(offs.begin(), offs.end(), o);
+        if (it == offs.end() || *it != o) {
+          if ((int)offs.size() == dev::kMaxDiagDev) return false;
+          offs.insert(it, o);
+        }
+      }
+    Dia D = build_dia_window(R, row_begin, n_rows, offs);
+    if (!D.ok) return false;
+    win.upload(D, s);
+    win_off = offs;
+    return true;
+  }
   const DevMat& rows_of_A() const { return (symmetric || block) ? colrows : *arows; }
   const Csc& host_rows_of_A() const { return symmetric ? M : MT; }  // CSC whose column k = row k of A
 
@@ -551,7 +574,7 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
-  o->fuse = 1 | 4;  // zero-guess sweep and streaming legs on; prolongation fusion (bit 1) measured slower
+  o->fuse = 1 | 4 | 16;  // zero-guess sweep, streaming legs, coarse tail; prolongation fusion (bit 1) measured slower
 }
 
 }  // namespace
@@ -595,6 +618,7 @@ struct LevelState {
   int n_own = 0;  // e - s
   int n_mat = 0;  // operator / rhs rows held: n_own (+ ghost rows, clipped at the last row)
   DevBuf<double> u, f, tmp;
+  DevBuf<double> fw;  // sharded levels with fused legs: f on the whole window [s - halo_lo, e + halo_hi)
   double* u_own() const { return u.p + halo_lo; }
   double* tmp_own() const { return tmp.p + halo_lo; }
   int64_t n_vec() const { return (int64_t)halo_lo + n_own + halo_hi; }
@@ -627,8 +651,8 @@ struct amgb_hierarchy {
   // neighbours' base pointers, plus epoch flags; falls back to NCCL send/recv when unavailable
   bool p2p = false;
   struct PeerMap {
-    double* lo[2] = {nullptr, nullptr};  // rank g-1's u / tmp base
-    double* hi[2] = {nullptr, nullptr};  // rank g+1's u / tmp base
+    double* lo[3] = {nullptr, nullptr, nullptr};  // rank g-1's u / tmp / fw base
+    double* hi[3] = {nullptr, nullptr, nullptr};  // rank g+1's u / tmp / fw base
     int lo_halo_lo = 0, lo_n_own = 0;    // geometry of rank g-1's block on this level
   };
   std::vector<PeerMap> peers;
@@ -675,14 +699,15 @@ struct amgb_hierarchy {
     epochs.zero(stream);
     timed_out.alloc(1);
     timed_out.zero(stream);
-    // handles: per rank [flags, then u and tmp of every sharded level]
-    const int per_rank = 1 + 2 * n_sharded;
+    // handles: per rank [flags, then u, tmp and fw of every sharded level]
+    const int per_rank = 1 + 3 * n_sharded;
     const size_t hb = sizeof(cudaIpcMemHandle_t);  // 64 bytes = 8 doubles
     std::vector<cudaIpcMemHandle_t> mine(per_rank);
     bool ok = cudaIpcGetMemHandle(&mine[0], flags.p) == cudaSuccess;
     for (int l = 0; l < n_sharded && ok; ++l) {
-      ok = ok && cudaIpcGetMemHandle(&mine[1 + 2 * l], lv[l].u.p) == cudaSuccess;
-      ok = ok && cudaIpcGetMemHandle(&mine[2 + 2 * l], lv[l].tmp.p) == cudaSuccess;
+      ok = ok && cudaIpcGetMemHandle(&mine[1 + 3 * l], lv[l].u.p) == cudaSuccess;
+      ok = ok && cudaIpcGetMemHandle(&mine[2 + 3 * l], lv[l].tmp.p) == cudaSuccess;
+      ok = ok && cudaIpcGetMemHandle(&mine[3 + 3 * l], lv[l].fw.p) == cudaSuccess;
     }
     cudaGetLastError();
     // all-gather (handles, ok flag) through NCCL on a device staging buffer
@@ -718,9 +743,9 @@ struct amgb_hierarchy {
     if (g > 0) mapped = mapped && (peer_flags_lo = (unsigned long long*)open(g - 1, 0));
     if (g + 1 < G) mapped = mapped && (peer_flags_hi = (unsigned long long*)open(g + 1, 0));
     for (int l = 0; l < n_sharded && mapped; ++l) {
-      for (int v = 0; v < 2; ++v) {
-        if (g > 0) mapped = mapped && (peers[l].lo[v] = (double*)open(g - 1, 1 + 2 * l + v));
-        if (g + 1 < G) mapped = mapped && (peers[l].hi[v] = (double*)open(g + 1, 1 + 2 * l + v));
+      for (int v = 0; v < 3; ++v) {
+        if (g > 0) mapped = mapped && (peers[l].lo[v] = (double*)open(g - 1, 1 + 3 * l + v));
+        if (g + 1 < G) mapped = mapped && (peers[l].hi[v] = (double*)open(g + 1, 1 + 3 * l + v));
       }
       if (g > 0) {
         peers[l].lo_halo_lo = plan.halo_lo[l];
@@ -765,7 +790,7 @@ struct amgb_hierarchy {
     const int dn_cnt = plan.halo_lo[l];  // what rank g+1 keeps below its block = my last rows
     ++halo_exchanges_per_vcycle;
     if (p2p) {
-      const int v = (base == S.u.p) ? 0 : 1;
+      const int v = (base == S.u.p) ? 0 : (base == S.tmp.p ? 1 : 2);
       const int site = site_cursor++;
       if (site >= kMaxSites) throw ApiError(AMGB_ESTATE, "too many halo-exchange sites");
       dev::HaloSide lo{}, hi{};
@@ -911,19 +936,8 @@ struct amgb_hierarchy {
     const size_t lbytes = sizeof(double) * (size_t)nc * std::max(bw, 1);
     const size_t cap = 200 * 1024;
     if (bw >= 1 && bw <= 8 && xbytes + lbytes <= 48 * 1024) {
-      const size_t smem = xbytes + lbytes;
-      double* fL = lv[L - 1].f.p;
-      double* uL = lv[L - 1].u.p;
-      switch (bw) {
-        case 1: LAUNCH(dev::k_banded_ldlt_solve_serial<1>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-        case 2: LAUNCH(dev::k_banded_ldlt_solve_serial<2>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-        case 3: LAUNCH(dev::k_banded_ldlt_solve_serial<3>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-        case 4: LAUNCH(dev::k_banded_ldlt_solve_serial<4>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-        case 5: LAUNCH(dev::k_banded_ldlt_solve_serial<5>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-        case 6: LAUNCH(dev::k_banded_ldlt_solve_serial<6>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-        case 7: LAUNCH(dev::k_banded_ldlt_solve_serial<7>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-        default: LAUNCH(dev::k_banded_ldlt_solve_serial<8>, 1, 32, smem, s, dL.p, dd.p, nc, fL, uL); break;
-      }
+      LAUNCH(dev::k_banded_ldlt_solve_serial, 1, 128, xbytes + lbytes, s, dL.p, dd.p, nc, bw, lv[L - 1].f.p,
+             lv[L - 1].u.p);
       return;
     }
     if (bw <= 31 && xbytes <= cap) {
@@ -1046,12 +1060,69 @@ struct amgb_hierarchy {
     G.ok = false;
     if (!(opt.fuse & 12) || opt.smoother != AMGB_SMOOTHER_JACOBI || opt.smoother_iters < 1 || l + 1 >= L) return;
     const LevelState& S = lv[l];
-    if (S.sharded || !S.tmp.p) return;
-    const DevMat& A = ops[l]->rows_of_A();
-    if (!A.is_dia || A.dia.n_diag > 10 || A.dia.rows.p) return;
+    if (!S.tmp.p) return;
     const int kind_down = (l == 0) ? leg::DOWN_U : leg::DOWN_ZERO;
     const int nu = (int)opt.smoother_iters;
     G.kind_down = kind_down;
+    if (S.sharded) {
+      // row block + ghost rows: the streaming kernels run on the rank's window of the level
+      const DevDia& W = ops[l]->win;
+      if (!(opt.fuse & 4) || nu != 2 || !W.val.p || W.n_diag > 10) return;
+      leg::Plan st = leg::plan_leg(leg::UP, nu, (int)n[l], W.n_diag, ops[l]->win_off.data(), 148, 200 * 1024);
+      if (!st.ok || !(st.P.m < st.P.n) || st.P.rho != 1) return;
+      int wmax = 0;
+      for (int o : ops[l]->win_off) wmax = std::max(wmax, std::abs(o));
+      // three chained stencil stages + the restriction's neighbours reach 3 wmax + 1 rows out
+      if (S.halo_lo < 3 * wmax + 4 || S.halo_hi < 3 * wmax + 4) return;  // ghost zone too thin
+      unsigned mask = 0;
+      for (int d = 0; d < W.n_diag; ++d) mask |= 1u << ((st.P.line_a[d] + 1) * 3 + st.P.delta[d] + 1);
+      sleg::Params dummy{};
+      if (!sleg_dispatch(kind_down, mask, dummy, nullptr, 0) || !sleg_dispatch(sleg::UP, mask, dummy, nullptr, 0)) return;
+      int n_sm = 148;
+      CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+      const LevelState& C = lv[l + 1];
+      auto plan = [&](int kind, int NS, int X) {
+        int wps = 12;
+        sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
+        const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", wps);
+        sleg::Params P{};
+        P.base = (int)(S.s - S.halo_lo);
+        P.n_global = (int)n[l];
+        P.own_begin = S.halo_lo;
+        P.own_end = S.halo_lo + S.n_own;
+        P.cbase = C.sharded ? (int)(C.s - C.halo_lo) : 0;
+        P.n_e = C.sharded ? (int)C.n_vec() : (int)n[l + 1];
+        P.n = (int)S.n_vec();
+        P.m = st.P.m;
+        P.n_lines = (P.n + P.m - 1) / P.m;
+        P.Wu = 32 - 2 * (NS + X);
+        P.n_strips = (P.m + P.Wu - 1) / P.Wu;
+        const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / 8));
+        P.LJ = (P.n_lines + chunks - 1) / chunks;
+        P.n_chunks = (P.n_lines + P.LJ - 1) / P.LJ;
+        P.n_warps = P.n_strips * P.n_chunks;
+        P.ld = W.ld;
+        P.n_coarse = (int)n[l + 1];
+        P.omega = opt.omega;
+        P.val = W.val.p;
+        P.f = S.fw.p;
+        return P;
+      };
+      G.sdown = plan(kind_down, kind_down == leg::DOWN_U ? nu + 1 : nu, 1);
+      G.sdown.uin = S.u.p;
+      G.sdown.uout = S.tmp.p;
+      G.sdown.fc = C.sharded ? C.fw.p : C.f.p;
+      G.sup = plan(sleg::UP, nu, 0);
+      G.sup.uin = S.tmp.p;
+      G.sup.e = C.u.p;
+      G.sup.uout = S.u.p;
+      G.mask = mask;
+      G.stream = true;
+      G.ok = true;
+      return;
+    }
+    const DevMat& A = ops[l]->rows_of_A();
+    if (!A.is_dia || A.dia.n_diag > 10 || A.dia.rows.p) return;
     if ((opt.fuse & 4) && nu == 2) {
       // line structure from the TMA-ring planner; the streaming kernels need rho == 1
       leg::Plan st = leg::plan_leg(leg::UP, nu, (int)n[l], A.dia.n_diag, A.dia.off, 148, 200 * 1024);
@@ -1067,6 +1138,12 @@ struct amgb_hierarchy {
             sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
             const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", wps);
             sleg::Params P{};
+            P.base = 0;
+            P.n_global = (int)n[l];
+            P.own_begin = 0;
+            P.own_end = (int)n[l];
+            P.cbase = 0;
+            P.n_e = (int)n[l + 1];
             P.n = (int)n[l];
             P.m = st.P.m;
             P.n_lines = st.P.n_lines;
@@ -1139,14 +1216,80 @@ struct amgb_hierarchy {
   }
   bool leg_ok(int l) const { return l >= 0 && l < (int)legs.size() && legs[l].ok; }
 
+  // ---- coarse tail (k_coarse_tail): levels [tail_first, L) of a damped-Jacobi cycle in one launch
+  int tail_first = -1;
+  dev::TailParams tail{};
+  size_t tail_smem = 0;
+  void prepare_tail() {
+    tail_first = -1;
+    if (!(opt.fuse & 16) || opt.smoother != AMGB_SMOOTHER_JACOBI || opt.smoother_iters < 1 || L < 2 ||
+        !opt.skip_dead_coarse_smooth)
+      return;
+    const int bw = factor.bw, nc = factor.n;
+    const size_t smem = sizeof(double) * (size_t)nc * (std::max(bw, 1) + 1);
+    if (bw < 1 || bw > 8 || smem > 200 * 1024) return;
+    const int64_t max_rows = env_int("AMGB_TAIL_ROWS", 6000);
+    int first = L - 1;  // the coarsest level alone is just the solve
+    while (first - 1 >= 1 && first - 1 >= L - 1 - dev::kTailMaxLevels && n[first - 1] <= max_rows) {
+      const int l = first - 1;
+      const LevelState& S = lv[l];
+      const DevMat& A = ops[l]->rows_of_A();
+      bool has_diag = false;
+      if (A.is_dia)
+        for (int d = 0; d < A.dia.n_diag; ++d) has_diag |= (A.dia.off[d] == 0);
+      if (S.sharded || !S.tmp.p || !A.is_dia || A.dia.n_diag > 10 || A.dia.rows.p || !has_diag) break;
+      first = l;
+    }
+    if (first >= L - 1) return;  // nothing to fuse
+    tail = dev::TailParams{};
+    tail.n_tail = L - 1 - first;
+    tail.nu = (int)opt.smoother_iters;
+    tail.omega = opt.omega;
+    tail.nc = nc;
+    tail.bw = bw;
+    tail.L = dL.p;
+    tail.d = dd.p;
+    tail.f_c = lv[L - 1].f.p;
+    tail.u_c = lv[L - 1].u.p;
+    for (int l = first; l < L - 1; ++l) {
+      dev::TailLevel& V = tail.lv[l - first];
+      const DevMat& A = ops[l]->rows_of_A();
+      V.A = A.dia.view();
+      V.A.mask = nullptr;  // every diagonal is read (the per-slice masks do not pay on tiny levels)
+      V.A.n_rows = (int)n[l];
+      V.diag_d = 0;
+      for (int d = 0; d < A.dia.n_diag; ++d)
+        if (A.dia.off[d] == 0) V.diag_d = d;
+      V.n = (int)n[l];
+      V.n_coarse = (int)n[l + 1];
+      V.f = lv[l].f.p;
+      V.u = lv[l].u.p;
+      V.tmp = lv[l].tmp.p;
+      V.f_coarse = lv[l + 1].f.p;
+    }
+    tail_smem = smem;
+    if (smem > 48 * 1024)
+      CUDA_CHECK(cudaFuncSetAttribute(dev::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tail_first = first;
+  }
+
   void enqueue_vcycle(cudaStream_t s) {
     halo_exchanges_per_vcycle = 0;
     site_cursor = 0;  // sites 0 .. k-1 belong to the V-cycle, in the same order on every rank
-    for (int l = 0; l < L; ++l) {
+    const int lt = (tail_first > 0) ? tail_first : L;  // levels [lt, L) run inside k_coarse_tail
+    for (int l = 0; l < lt; ++l) {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
       if (leg_ok(l)) {  // sweeps + residual + restriction in one pass: u_l -> tmp_l, f_{l+1}
-        leg_down(l, s);
+        if (lv[l].sharded) {
+          // ghost rows of the leg's input: the iterate on level 0, the right-hand side below
+          exchange(l, l == 0 ? lv[l].u.p : lv[l].fw.p, s);
+          leg_down(l, s);
+          if (!lv[l + 1].sharded)  // first agglomerated level: every rank gets the whole right-hand side
+            allgather_blocks(lv[l + 1].f.p, coarse_block_start, s);
+        } else {
+          leg_down(l, s);
+        }
         continue;
       }
       // a fused finer level does not zero u_l (its own coarse levels never read it)
@@ -1156,10 +1299,18 @@ struct amgb_hierarchy {
       // on the coarsest level the reference also forms the residual (:272-274);
       // it is stored in a private member without a getter and never read.
     }
-    coarse_solve(s);
-    for (int l = L - 2; l >= 0; --l) {
-      if (leg_ok(l)) leg_up(l, s);  // tmp_l + P u_{l+1}, sweeps -> u_l
-      else smooth(l, s, false, /*with_prolong=*/true);
+    if (lt < L) LAUNCH(dev::k_coarse_tail, 1, 1024, tail_smem, s, tail);
+    else coarse_solve(s);
+    for (int l = std::min(lt, L - 1) - 1; l >= 0; --l) {
+      if (leg_ok(l)) {  // tmp_l + P u_{l+1}, sweeps -> u_l
+        if (lv[l].sharded) {
+          exchange(l, lv[l].tmp.p, s);
+          if (lv[l + 1].sharded) exchange(l + 1, lv[l + 1].u.p, s);
+        }
+        leg_up(l, s);
+      } else {
+        smooth(l, s, false, /*with_prolong=*/true);
+      }
     }
   }
   void build_graph() {
@@ -1246,6 +1397,11 @@ struct amgb_hierarchy {
   }
   void upload_f(int l, const double* full) {
     LevelState& S = lv[l];
+    if (S.sharded && S.fw.p) {
+      const int64_t lo = std::max<int64_t>(0, S.s - S.halo_lo), hi = std::min<int64_t>(n[l], S.e + S.halo_hi);
+      CUDA_CHECK(cudaMemcpyAsync(S.fw.p + (lo - (S.s - S.halo_lo)), full + lo, sizeof(double) * (hi - lo),
+                                 cudaMemcpyHostToDevice, stream));
+    }
     CUDA_CHECK(cudaMemcpyAsync(S.f.p, full + S.s, sizeof(double) * S.n_mat, cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
   }
@@ -1544,7 +1700,40 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
     if (o.smoother != AMGB_SMOOTHER_JACOBI)
       throw std::invalid_argument("the row-block sharded V-cycle supports the damped-Jacobi smoother only "
                                   "(lexicographic Gauss-Seidel is a single-GPU path)");
-    h->plan = make_partition_plan(h->n, half_bw, world, min_rows_per_rank);
+    // With the fused legs on, only levels whose operator is a 3 x 3 line stencil are worth
+    // sharding (they run as streaming legs on the rank's window); the levels below, a few
+    // hundred thousand rows at most, are agglomerated.
+    int max_sharded = 1 << 30;
+    if ((o.fuse & 4) && o.smoother_iters == 2) {
+      max_sharded = 0;
+      for (int l = 0; l + 1 < L; ++l) {
+        const Csc& M = mats[l];
+        std::vector<int> offs;
+        bool banded = true;
+        for (int c = 0; c < M.cols && banded; ++c)
+          for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p) {
+            if (M.val[p] == 0.0) continue;
+            const int off = M.rowidx[p] - c;
+            auto it = std::lower_bound(offs.begin(), offs.end(), off);
+            if (it == offs.end() || *it != off) {
+              if ((int)offs.size() == 10) {
+                banded = false;
+                break;
+              }
+              offs.insert(it, off);
+            }
+          }
+        if (!banded || offs.empty()) break;
+        leg::Plan st = leg::plan_leg(leg::UP, 2, (int)h->n[l], (int)offs.size(), offs.data(), 148, 200 * 1024);
+        if (!st.ok || !(st.P.m < st.P.n) || st.P.rho != 1) break;
+        unsigned mask = 0;
+        for (size_t d = 0; d < offs.size(); ++d) mask |= 1u << ((st.P.line_a[d] + 1) * 3 + st.P.delta[d] + 1);
+        if (mask != sleg::kMask5 && mask != sleg::kMask7a && mask != sleg::kMask7b && mask != sleg::kMask9) break;
+        max_sharded = l + 1;
+      }
+      if (max_sharded == 0) max_sharded = 1 << 30;  // no streamable level: the per-operator kernels shard as before
+    }
+    h->plan = make_partition_plan(h->n, half_bw, world, min_rows_per_rank, max_sharded);
     h->n_sharded = h->plan.n_sharded;
     if (h->n_sharded > 0) {
       h->coarse_block_start.resize(world + 1);
@@ -1585,9 +1774,24 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
       S.tmp.alloc(S.n_vec() + 8);
       S.tmp.zero(s);
     }
+    if (S.sharded) {
+      S.fw.alloc(S.n_vec() + 8);
+      S.fw.zero(s);
+      // window mirror of the operator for the fused legs (block + ghost rows on both sides)
+      if ((o.fuse & 4) && o.smoother == AMGB_SMOOTHER_JACOBI && o.smoother_iters == 2)
+        h->ops[l]->build_window((int)(S.s - S.halo_lo), (int)S.n_vec(), s);
+    }
     if (!(l + 1 == L && o.skip_dead_coarse_smooth)) h->prepare_smoother(l);
   }
   for (int l = 0; l < L; ++l) h->prepare_legs(l);
+  {
+    // sharded levels hand each other right-hand sides in the window layout: fused legs on all of
+    // them or on none
+    bool all = true;
+    for (int l = 0; l < h->n_sharded; ++l) all = all && h->leg_ok(l);
+    if (!all)
+      for (int l = 0; l < h->n_sharded; ++l) h->legs[l].ok = false;
+  }
   h->upload_f(0, b);
   h->partial.alloc(std::max(1, blocks_for(h->lv[0].n_own, 256)));
   h->scalar.alloc(1);
@@ -1595,6 +1799,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
   h->dd.upload(h->factor.d, s);
   h->dwork.alloc(h->factor.n);
   CUDA_CHECK(cudaStreamSynchronize(s));
+  h->prepare_tail();  // needs the factor on the device
   h->setup_p2p();
   *out = h.release();
 }
@@ -1932,6 +2137,7 @@ int amgb_coarse_solve(amgb_hierarchy* h) {
   });
 }
 
+int amgb_hierarchy_tail_first(const amgb_hierarchy* h) { return h ? h->tail_first : -1; }
 int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level) {
   return (h && h->leg_ok(level)) ? 1 : 0;
 }
@@ -2004,7 +2210,7 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
   return guarded([&] {
     if (!h || !ms_out || reps < 1) throw std::invalid_argument("bad argument");
     h->check_level(level, kind >= 2);
-    if (kind >= 2) h->require_whole(level);
+    if (kind == 2 || kind == 3) h->require_whole(level);
     if (kind == 4 || kind == 5) {
       // fused down / up leg of this level; they work on the level state, which is restored
       if (!h->leg_ok(level)) throw ApiError(AMGB_ESTATE, "level has no fused legs");

@@ -356,11 +356,41 @@ Dia build_dia_block(const Csc& M, int row_begin, int n_rows) {
   return D;
 }
 
+// Rows [row_begin, row_begin + n_rows) of M, local numbering; rows outside [0, M.cols) are empty.
+// `offsets` (ascending) fixes the diagonal order, so every rank of a sharded level uses the same
+// stencil layout whatever part of the operator its window sees.
+Dia build_dia_window(const Csc& M, int row_begin, int n_rows, const std::vector<int>& offsets) {
+  Dia D;
+  D.ok = true;
+  D.n_rows = n_rows;
+  D.n_cols = M.rows;
+  D.ld = (n_rows + 31) / 32 * 32;
+  D.n_diag = static_cast<int>(offsets.size());
+  D.off = offsets;
+  D.val.assign(static_cast<size_t>(D.n_diag) * D.ld, 0.0);
+  for (int t = 0; t < n_rows; ++t) {
+    const int r = row_begin + t;
+    if (r < 0 || r >= M.cols) continue;
+    for (int p = M.colptr[r]; p < M.colptr[r + 1]; ++p) {
+      if (M.val[p] == 0.0) continue;
+      const int o = M.rowidx[p] - r;
+      auto it = std::lower_bound(offsets.begin(), offsets.end(), o);
+      if (it == offsets.end() || *it != o) {
+        D.ok = false;
+        return D;
+      }
+      D.val[static_cast<size_t>(it - offsets.begin()) * D.ld + t] = M.val[p];
+      ++D.nnz;
+    }
+  }
+  return D;
+}
+
 // ------------------------------------------------------------------ partition plan
 
 PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
                                   const std::vector<int>& half_bandwidth, int world,
-                                  int64_t min_rows_per_rank) {
+                                  int64_t min_rows_per_rank, int max_sharded) {
   PartitionPlan P;
   P.world = world;
   P.n_levels = static_cast<int>(level_sizes.size());
@@ -368,14 +398,16 @@ PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
   if (world <= 1) return P;
   // deepest prefix of levels that is worth sharding (never the coarsest level)
   int ns = 0;
-  while (ns + 1 < P.n_levels && level_sizes[ns] / world >= min_rows_per_rank) ++ns;
+  while (ns + 1 < P.n_levels && ns < max_sharded && level_sizes[ns] / world >= min_rows_per_rank) ++ns;
   // shrink until every block comfortably contains its halos
   for (; ns > 0; --ns) {
     bool ok = true;
     int ghost = 0;
     for (int l = ns - 1; l >= 0 && ok; --l) {
       ghost = 2 * ghost + 1;
-      const int64_t need = 4ll * (half_bandwidth[l] + ghost + 2) + (1ll << ns);
+      // the fused legs recompute three chained stencil stages on the ghost rows: 3 (w + 1) + 4
+      const int64_t need = std::max<int64_t>(4ll * (half_bandwidth[l] + ghost + 2),
+                                             2ll * (3ll * (half_bandwidth[l] + 1) + 4 + ghost)) + (1ll << ns);
       if (level_sizes[l] / world < need) ok = false;
     }
     if (ok) break;
@@ -399,8 +431,11 @@ PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
     P.ghost[l] = ghost;
     // +2: the fused prolongation sweep evaluates u + P e on the fine halo, which reaches one
     // coarse entry further than the coarse operator's own half-bandwidth
-    P.halo_lo[l] = half_bandwidth[l] + 2;
-    P.halo_hi[l] = half_bandwidth[l] + ghost + 2;
+    // 3 (w + 1) + 4 ghost rows on each side let the fused legs (stream_leg.cuh) recompute their
+    // three chained stencil stages there; the per-operator kernels need w + 2 (+ ghost above)
+    const int fused = 3 * (half_bandwidth[l] + 1) + 4;
+    P.halo_lo[l] = std::max(half_bandwidth[l] + 2, fused);
+    P.halo_hi[l] = std::max(half_bandwidth[l] + ghost + 2, fused + ghost);
   }
   return P;
 }

@@ -96,6 +96,9 @@ Dia build_dia(const Csc& M, const std::vector<int>* rows = nullptr);
 // local row t multiplies x_local[t + off[d] + x_shift], x_local being this
 // rank's halo-extended vector (x_shift = number of halo elements below).
 Dia build_dia_block(const Csc& M, int row_begin, int n_rows);
+// Same for a window that may reach past the ends of the matrix (those rows stay empty), with the
+// diagonal order given by `offsets` (ascending); !ok when an entry falls outside them.
+Dia build_dia_window(const Csc& M, int row_begin, int n_rows, const std::vector<int>& offsets);
 
 // ---- row-block partition of the fine levels over the ranks of one node ----
 // Level l < n_sharded is split into contiguous row blocks [start[l][g], start[l][g+1]);
@@ -113,9 +116,10 @@ struct PartitionPlan {
   std::vector<std::vector<int64_t>> start;  // [level][rank 0..world]
   std::vector<int> halo_lo, halo_hi, ghost; // per sharded level
 };
+// max_sharded caps the number of sharded levels (the rest is agglomerated).
 PartitionPlan make_partition_plan(const std::vector<int64_t>& level_sizes,
                                   const std::vector<int>& half_bandwidth, int world,
-                                  int64_t min_rows_per_rank);
+                                  int64_t min_rows_per_rank, int max_sharded = 1 << 30);
 
 // ---- Gauss-Seidel wavefront schedule on the pruned dependency DAG ----
 // forward: row k depends on rows j<k with M(j,k) != 0 (column k of M used as

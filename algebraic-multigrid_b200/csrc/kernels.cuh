@@ -766,61 +766,203 @@ __global__ void __launch_bounds__(32) k_banded_ldlt_solve_warp(const double* __r
 }
 
 // Same solve for half-bandwidth BW <= 8 as a plain recurrence: one thread keeps the last BW
-// results in registers, so a row costs one short multiply-subtract chain (~20 cycles) instead
-// of the shuffle round trips of the warp kernel (~180 cycles per pivot).  Every entry receives
-// its updates in the order of k_banded_ldlt_solve (ascending pivot forward, descending pivot
-// backward), i.e. the oracle's order.  Factor, diagonal and vector are staged in shared memory
-// by the whole warp; the division pass is spread over the lanes.
+// results in registers, so a row costs one short multiply-subtract chain instead of the
+// shuffle round trips of the warp kernel.  Every entry receives its updates in the order of
+// k_banded_ldlt_solve (ascending pivot forward, descending pivot backward), i.e. the oracle's
+// order.  Factor and vector are staged in shared memory by all threads of the block (sm holds
+// n * (BW + 1) doubles); the division pass is spread over the threads.  Block-wide call.
 template <int BW>
-__global__ void __launch_bounds__(32) k_banded_ldlt_solve_serial(const double* __restrict__ L,
-                                                                 const double* __restrict__ d, int n,
-                                                                 const double* __restrict__ f,
-                                                                 double* __restrict__ x_out) {
-  extern __shared__ double sm[];
-  double* y = sm;               // n
-  double* sL = sm + n;          // n * BW
-  const int lane = threadIdx.x;
-  for (int i = lane; i < n * BW; i += 32) sL[i] = L[i];
-  for (int i = lane; i < n; i += 32) y[i] = f[i];
-  __syncwarp();
-  if (lane == 0) {
-    double win[BW];  // win[t - 1] = y[r - t]
+__device__ __forceinline__ void ldlt_serial_block(double* sm, const double* __restrict__ L,
+                                                  const double* __restrict__ d, int n,
+                                                  const double* __restrict__ f, double* __restrict__ x_out) {
+  double* y = sm;       // n
+  double* sL = sm + n;  // n * BW
+  const int t = threadIdx.x, T = blockDim.x;
+  for (int i = t; i < n * BW; i += T) sL[i] = L[i];
+  for (int i = t; i < n; i += T) y[i] = __ldcg(f + i);
+  __syncthreads();
+  if (t == 0) {
+    double win[BW];  // win[k - 1] = y[r - k]
 #pragma unroll
-    for (int t = 0; t < BW; ++t) win[t] = 0.0;
+    for (int k = 0; k < BW; ++k) win[k] = 0.0;
 #pragma unroll 4
     for (int r = 0; r < n; ++r) {
       double acc = y[r];
       const double* lr = sL + (size_t)r * BW;
 #pragma unroll
-      for (int t = BW; t >= 1; --t)
-        if (r - t >= 0) acc = __dsub_rn(acc, __dmul_rn(lr[BW - t], win[t - 1]));
+      for (int k = BW; k >= 1; --k)
+        if (r - k >= 0) acc = __dsub_rn(acc, __dmul_rn(lr[BW - k], win[k - 1]));
 #pragma unroll
-      for (int t = BW - 1; t >= 1; --t) win[t] = win[t - 1];
+      for (int k = BW - 1; k >= 1; --k) win[k] = win[k - 1];
       win[0] = acc;
       y[r] = acc;
     }
   }
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) y[i] = __ddiv_rn(y[i], d[i]);
-  __syncwarp();
-  if (lane == 0) {
-    double win[BW];  // win[t - 1] = x[c + t]
+  __syncthreads();
+  for (int i = t; i < n; i += T) y[i] = __ddiv_rn(y[i], d[i]);
+  __syncthreads();
+  if (t == 0) {
+    double win[BW];  // win[k - 1] = x[c + k]
 #pragma unroll
-    for (int t = 0; t < BW; ++t) win[t] = 0.0;
+    for (int k = 0; k < BW; ++k) win[k] = 0.0;
 #pragma unroll 4
     for (int c = n - 1; c >= 0; --c) {
       double acc = y[c];
 #pragma unroll
-      for (int t = BW; t >= 1; --t)
-        if (c + t < n) acc = __dsub_rn(acc, __dmul_rn(sL[(size_t)(c + t) * BW + (BW - t)], win[t - 1]));
+      for (int k = BW; k >= 1; --k)
+        if (c + k < n) acc = __dsub_rn(acc, __dmul_rn(sL[(size_t)(c + k) * BW + (BW - k)], win[k - 1]));
 #pragma unroll
-      for (int t = BW - 1; t >= 1; --t) win[t] = win[t - 1];
+      for (int k = BW - 1; k >= 1; --k) win[k] = win[k - 1];
       win[0] = acc;
       y[c] = acc;
     }
   }
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) x_out[i] = y[i];
+  __syncthreads();
+  for (int i = t; i < n; i += T) x_out[i] = y[i];
+  __syncthreads();
+}
+__device__ __forceinline__ void ldlt_serial_block_bw(int bw, double* sm, const double* L, const double* d, int n,
+                                                     const double* f, double* x_out) {
+  switch (bw) {
+    case 1: ldlt_serial_block<1>(sm, L, d, n, f, x_out); break;
+    case 2: ldlt_serial_block<2>(sm, L, d, n, f, x_out); break;
+    case 3: ldlt_serial_block<3>(sm, L, d, n, f, x_out); break;
+    case 4: ldlt_serial_block<4>(sm, L, d, n, f, x_out); break;
+    case 5: ldlt_serial_block<5>(sm, L, d, n, f, x_out); break;
+    case 6: ldlt_serial_block<6>(sm, L, d, n, f, x_out); break;
+    case 7: ldlt_serial_block<7>(sm, L, d, n, f, x_out); break;
+    default: ldlt_serial_block<8>(sm, L, d, n, f, x_out); break;
+  }
+}
+__global__ void __launch_bounds__(128) k_banded_ldlt_solve_serial(const double* __restrict__ L,
+                                                                  const double* __restrict__ d, int n, int bw,
+                                                                  const double* __restrict__ f,
+                                                                  double* __restrict__ x_out) {
+  extern __shared__ double sm[];
+  ldlt_serial_block_bw(bw, sm, L, d, n, f, x_out);
+}
+
+// ------------------------------------------------------------------ coarse tail of the V-cycle
+// The levels below a size threshold hold a few thousand rows each: every kernel on them is pure
+// launch latency (~4 us) and there are six per level.  This kernel runs the WHOLE tail of a
+// damped-Jacobi cycle -- for every tail level the pre-smoothing sweeps, residual and
+// restriction, then the coarsest solve, then for every tail level prolongation + add and the
+// post-smoothing sweeps (multigrid.hpp:265-302) -- in ONE block, with block barriers where the
+// per-operator kernels have launch boundaries.  Vectors stay in global memory (L2-resident);
+// per-row arithmetic is that of k_jacobi_zero / k_jacobi / k_residual / k_restrict /
+// k_prolong_add, so every bit is unchanged.
+constexpr int kTailMaxLevels = 12;
+struct TailLevel {
+  DiaView A;   // rows of A (n_diag <= 10)
+  int diag_d;  // index of the main diagonal
+  int n, n_coarse;
+  const double* f;
+  double* u;
+  double* tmp;
+  double* f_coarse;  // next level's right-hand side
+};
+struct TailParams {
+  int n_tail;   // tail levels that are smoothed (the coarsest level follows them)
+  int nu;       // Jacobi sweeps per smooth call
+  double omega;
+  // coarsest level
+  int nc, bw;
+  const double* L;
+  const double* d;
+  const double* f_c;
+  double* u_c;
+  TailLevel lv[kTailMaxLevels];
+};
+
+// Vectors the block itself wrote earlier in the launch are read with ld.global.cg (L2), never
+// through the non-coherent path.
+template <int ND>
+__device__ __forceinline__ void tail_jacobi(const TailLevel& V, const double* src, double* dst, double omega) {
+  DiaViewT<ND> A;
+  static_cast<DiaView&>(A) = V.A;
+  for (int t = threadIdx.x; t < V.n; t += blockDim.x) {
+    double acc = __ldcg(V.f + t), diag = 0.0;
+    for_each_entry_x(A, t, t, [&](int c) { return __ldcg(src + c); }, [&](int c, double a, double xv) {
+      if (c == t) diag = a;
+      acc = __dsub_rn(acc, __dmul_rn(a, xv));
+    });
+    const double ut = __ldcg(src + t);
+    dst[t] = (diag == 0.0) ? ut : __dadd_rn(ut, __dmul_rn(omega, __ddiv_rn(acc, diag)));
+  }
+}
+template <int ND>
+__device__ __forceinline__ void tail_residual(const TailLevel& V, const double* x, double* r) {
+  DiaViewT<ND> A;
+  static_cast<DiaView&>(A) = V.A;
+  for (int t = threadIdx.x; t < V.n; t += blockDim.x) {
+    double acc = __ldcg(V.f + t);
+    for_each_entry_x(A, t, t, [&](int c) { return __ldcg(x + c); },
+                     [&](int, double a, double xv) { acc = __dsub_rn(acc, __dmul_rn(a, xv)); });
+    r[t] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_coarse_tail(const __grid_constant__ TailParams P) {
+  extern __shared__ double sm[];
+  const int T = blockDim.x;
+  // ---- down: u_l = 0 -> nu sweeps -> residual -> restriction.  Sweeps alternate tmp, u, tmp, ...
+  // so that after the 2 nu sweeps of a whole cycle the iterate of the level sits in u.
+  for (int l = 0; l < P.n_tail; ++l) {
+    const TailLevel& V = P.lv[l];
+    double* buf[2] = {V.tmp, V.u};
+    for (int t = threadIdx.x; t < V.n; t += T) {  // first sweep from the zero guess (k_jacobi_zero)
+      const double diag = V.A.val[(size_t)V.diag_d * V.A.ld + t];
+      buf[0][t] = (diag == 0.0) ? 0.0 : __dmul_rn(P.omega, __ddiv_rn(__ldcg(V.f + t), diag));
+    }
+    __syncthreads();
+    for (int s = 1; s < P.nu; ++s) {
+      if (V.A.n_diag <= 6) tail_jacobi<6>(V, buf[(s - 1) & 1], buf[s & 1], P.omega);
+      else tail_jacobi<10>(V, buf[(s - 1) & 1], buf[s & 1], P.omega);
+      __syncthreads();
+    }
+    const double* x = buf[(P.nu - 1) & 1];
+    double* r = buf[P.nu & 1];
+    if (V.A.n_diag <= 6) tail_residual<6>(V, x, r);
+    else tail_residual<10>(V, x, r);
+    __syncthreads();
+    for (int J = threadIdx.x; J < V.n_coarse; J += T) {  // k_restrict
+      double acc = 0.0;
+      const int i = 2 * J;
+      if (i < V.n) acc = __dadd_rn(acc, __dmul_rn(0.5, __ldcg(r + i)));
+      if (i + 1 < V.n) acc = __dadd_rn(acc, __dmul_rn(1.0, __ldcg(r + i + 1)));
+      if (i + 2 < V.n) acc = __dadd_rn(acc, __dmul_rn(0.5, __ldcg(r + i + 2)));
+      V.f_coarse[J] = acc;
+    }
+    __syncthreads();
+  }
+  // ---- coarsest solve (multigrid.hpp:287-288)
+  ldlt_serial_block_bw(P.bw, sm, P.L, P.d, P.nc, P.f_c, P.u_c);
+  // ---- up: x += P e, nu sweeps, result in u
+  for (int l = P.n_tail - 1; l >= 0; --l) {
+    const TailLevel& V = P.lv[l];
+    double* buf[2] = {V.tmp, V.u};
+    double* x = buf[(P.nu - 1) & 1];
+    const double* e = (l + 1 < P.n_tail) ? P.lv[l + 1].u : P.u_c;
+    for (int t = threadIdx.x; t < V.n; t += T) {
+      double acc = 0.0;  // prolong_at with L2 loads
+      const int J = t >> 1;
+      if (t & 1) {
+        if (J < V.n_coarse) acc = __dadd_rn(acc, __dmul_rn(1.0, __ldcg(e + J)));
+      } else {
+        if (J - 1 >= 0 && J - 1 < V.n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, __ldcg(e + J - 1)));
+        if (J < V.n_coarse) acc = __dadd_rn(acc, __dmul_rn(0.5, __ldcg(e + J)));
+      }
+      x[t] = __dadd_rn(__ldcg(x + t), acc);
+    }
+    __syncthreads();
+    for (int s = 0; s < P.nu; ++s) {
+      const double* src = buf[(P.nu - 1 + s) & 1];
+      double* dst = buf[(P.nu + s) & 1];
+      if (V.A.n_diag <= 6) tail_jacobi<6>(V, src, dst, P.omega);
+      else tail_jacobi<10>(V, src, dst, P.omega);
+      __syncthreads();
+    }
+  }
 }
 
 }  // namespace dev

@@ -42,7 +42,17 @@ constexpr unsigned kMask7b = 0x0FEu;  // level 1 with m = its larger far offset:
 constexpr unsigned kMask9 = 0x1FFu;   // Galerkin levels >= 2
 
 struct Params {
-  int n;         // rows of the level
+  // The kernel works on a WINDOW of the level: local row k is global row base + k.  A whole level
+  // is the window [0, n) with base 0; a rank of the row-block sharded cycle passes its block plus
+  // the ghost rows on both sides (whose inputs a halo exchange has filled) and stores results for
+  // its own rows only -- the ghost rows are recomputed redundantly, like the lanes at a warp's edge.
+  int base;       // global row of local row 0 (may be negative: rows before the level start)
+  int n_global;   // rows of the level
+  int own_begin;  // local rows [own_begin, own_end) are stored
+  int own_end;
+  int cbase;      // global coarse index of fc[0] and e[0]
+  int n_e;        // entries of e / fc that exist locally
+  int n;         // rows of the window
   int m;         // line length
   int n_lines;   // ceil(n / m)
   int Wu;        // owned elements per warp (32 - 2H)
@@ -86,7 +96,8 @@ struct Leg {
 
   static __device__ __forceinline__ void load(Line& L, const Params& P, int g, int lane) {
     const int k = g + lane;
-    const bool ok = (k >= 0 && k < P.n);
+    const int kg = k + P.base;
+    const bool ok = (k >= 0 && k < P.n && kg >= 0 && kg < P.n_global);
     const double* vp = P.val + k;
 #pragma unroll
     for (int d = 0; d < ND; ++d) L.a[d] = ok ? __ldg(vp + (size_t)d * P.ld) : 0.0;
@@ -95,9 +106,10 @@ struct Leg {
     if (KIND == UP) {
       // (P e)[k]: odd k: 1 e[J]; even k: .5 e[J-1] + .5 e[J], J = k >> 1, terms outside
       // [0, n_coarse) absent (interpolator.hpp:118-125)
-      const int J = k >> 1;
-      L.e0 = (ok && !(k & 1) && J - 1 >= 0 && J - 1 < P.n_coarse) ? __ldg(P.e + J - 1) : 0.0;
-      L.e1 = (ok && J < P.n_coarse) ? __ldg(P.e + J) : 0.0;
+      const int J = kg >> 1, Jl = J - P.cbase;
+      L.e0 = (ok && !(kg & 1) && J - 1 >= 0 && J - 1 < P.n_coarse && Jl - 1 >= 0 && Jl - 1 < P.n_e)
+                 ? __ldg(P.e + Jl - 1) : 0.0;
+      L.e1 = (ok && J < P.n_coarse && Jl >= 0 && Jl < P.n_e) ? __ldg(P.e + Jl) : 0.0;
     }
   }
 
@@ -164,11 +176,11 @@ struct Leg {
     {
       const Line& L = S.R[P_ % RS];
       const int k = g1 + lane;
-      const double in = input(L, P, k);
+      const double in = input(L, P, k + P.base);
       S.w[0][0] = S.w[0][1];
       S.w[0][1] = S.w[0][2];
       S.w[0][2] = in;
-      if (S_OUT == 0 && own_lane && jj + 1 >= j0 && jj + 1 < j1 && k >= 0 && k < P.n) P.uout[k] = in;
+      if (S_OUT == 0 && own_lane && jj + 1 >= j0 && jj + 1 < j1 && k >= P.own_begin && k < P.own_end) P.uout[k] = in;
     }
 #pragma unroll
     for (int s = 1; s <= NS; ++s) {
@@ -176,14 +188,15 @@ struct Leg {
       const int j = jj - s + 1;
       const int k = g1 - s * m + lane;
       const double acc = stencil(L, S.w[s - 1][0], S.w[s - 1][1], S.w[s - 1][2]);
-      const bool own = own_lane && j >= j0 && j < j1 && k >= 0 && k < P.n;
+      const bool own = own_lane && j >= j0 && j < j1 && k >= P.own_begin && k < P.own_end;
       if (KIND != UP && s == NS) {
         // residual -> restriction: f_c[J] = (.5 r[2J] + r[2J+1]) + .5 r[2J+2]   (interpolator.hpp:64-68)
         const double rm = __shfl_up_sync(0xffffffffu, acc, 1);
         const double rp = __shfl_down_sync(0xffffffffu, acc, 1);
-        if (own && (k & 1)) {
-          const int J = (k - 1) >> 1;
-          if (J < P.n_coarse) P.fc[J] = __dadd_rn(__dadd_rn(__dmul_rn(0.5, rm), acc), __dmul_rn(0.5, rp));
+        const int kg = k + P.base;
+        if (own && (kg & 1)) {
+          const int J = (kg - 1) >> 1;
+          if (J < P.n_coarse) P.fc[J - P.cbase] = __dadd_rn(__dadd_rn(__dmul_rn(0.5, rm), acc), __dmul_rn(0.5, rp));
         }
       } else {
         const double diag = L.a[DC];

@@ -2,7 +2,7 @@
 """bench.py -- V-cycles/s of the B200-native multigrid V-cycle path.
 
 Workload (BASELINE.json metric / configs[2]): 2-D five-point Poisson on a
-4097x4097 interior grid, fp64, 16 levels (coarsest 511 DOF), damped-Jacobi
+4097x4097 interior grid, fp64, 18 levels (coarsest 127 DOF), damped-Jacobi
 smoother (omega 2/3, 2 pre + 2 post sweeps), device-resident V-cycles replayed
 as a CUDA graph.  One "step" is one V-cycle.  Prints ONE JSON line.
 
@@ -35,7 +35,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--n", type=int, default=4097, help="interior grid points per direction")
-    p.add_argument("--levels", type=int, default=0, help="0 = coarsen until <= 600 DOF")
+    p.add_argument("--levels", type=int, default=0, help="0 = coarsen until <= 200 DOF")
     p.add_argument("--smoother", default="jacobi", choices=["jacobi", "color", "gs"])
     p.add_argument("--eps", type=float, default=1.0, help="anisotropy of the +-n coupling")
     p.add_argument("--min-rows-per-rank", type=int, default=1 << 17,
@@ -48,7 +48,7 @@ def parse_args():
 def default_levels(n):
     import oracle as O  # closed-form size rule only
     sizes = [n * n]
-    while sizes[-1] > 600:
+    while sizes[-1] > 200:
         sizes.append(O.n_H_from_n_h(sizes[-1]))
     return len(sizes)
 
@@ -177,9 +177,12 @@ def run_b200(a):
     amg.lib().amgb_set_device(local)
     dist = None
     comm = None
+    # Libraries (NCCL's version banner, ...) write to the C-level stdout: route everything but
+    # the final JSON line to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
         def exchange_id(raw):
@@ -265,13 +268,13 @@ def run_b200(a):
     n1 = mg.get_n_dofs(1)
     r0, r1 = mg.local_range(0)
     survey0 = mg.pass_bytes(0)
-    fused0 = world == 1 and mg.fused_legs(0)
+    fused0 = mg.fused_legs(0)
     per_kernel = {}
     if fused0:
         # fused down leg of level 0 (sweeps + residual + restriction in one pass): operator,
         # f and u read once, smoothed u written once, coarse rhs written once
         kern_ms = mg.time_kernel(0, 4, warmup=3, reps=20)
-        bytes0 = mg.matrix_bytes(0) + 24 * N0 + 8 * n1
+        bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0) + 8 * ((r1 - r0) // 2)   # this rank's row block
         plan = mg.leg_plan(0)
         kname = "k_stream_leg" if plan["smem_bytes"] == 0 else "k_fused_leg"
         kdesc = "%s down leg (level 0: %d Jacobi sweeps + residual + restriction in one pass, %s layout)" % (
@@ -307,7 +310,7 @@ def run_b200(a):
     layout_bytes = 0
     for l in range(levels - 1):
         nl, nn = mg.get_n_dofs(l), mg.get_n_dofs(l + 1)
-        if world == 1 and mg.fused_legs(l):
+        if mg.fused_legs(l):
             down = mg.matrix_bytes(l) + (24 if l == 0 else 16) * nl + 8 * nn
             up = mg.matrix_bytes(l) + 24 * nl + 8 * nn
             layout_bytes += down + up
@@ -350,7 +353,7 @@ def run_b200(a):
                                       mg.halo_exchanges_per_vcycle()),
                    "mdof_per_s": vps * N0 / 1e6, "setup_s": setup_s,
                    "rss_after_timed_cycles": rss_after,
-                   "fused_legs": [bool(world == 1 and mg.fused_legs(l)) for l in range(levels - 1)],
+                   "fused_legs": [bool(mg.fused_legs(l)) for l in range(levels - 1)], "tail_first": mg.tail_first(),
                    "vcycle_layout_bytes": layout_bytes,
                    "vcycle_hbm_frac": (layout_bytes / (ms / a.steps * 1e-3) / 1e9 / peak) if world == 1 else None,
                    "vcycle_survey_formula_bytes": vbytes,
@@ -359,7 +362,7 @@ def run_b200(a):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": launches, "clocks": clocks,
     }
-    print(json.dumps(out))
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

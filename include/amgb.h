@@ -146,8 +146,12 @@ typedef struct amgb_options {
                                (default on): fused legs -- per level ONE kernel for
                                sweeps + residual + restriction (multigrid.hpp:268-282) and
                                ONE for prolongation + add + sweeps (:294-301), each reading
-                               the operator from HBM once.  The arithmetic, hence every bit
-                               of the result, is unchanged                               */
+                               the operator from HBM once (register-streaming kernels for
+                               operators that are 3 x 3 stencils over lines, two sweeps);
+                               bit 3 (default off): TMA-ring fused legs for the other banded
+                               levels; bit 4 (default on): the small coarse levels, the
+                               coarsest solve included, run in ONE kernel launch.  The
+                               arithmetic, hence every bit of the result, is unchanged   */
 } amgb_options;
 void amgb_options_default(amgb_options* opt);
 
@@ -259,6 +263,8 @@ int amgb_coarse_solve(amgb_hierarchy* h);
  * (= CTAs), strips, TMA lines in flight, threads per CTA, dynamic shared memory bytes, chained
  * stencil stages. */
 int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level);
+/* first level of the coarse tail that runs in one launch (option fuse bit 4), -1 if none */
+int amgb_hierarchy_tail_first(const amgb_hierarchy* h);
 int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info);
 
 /* counters: kernels launched by this library in this process, and per V-cycle */

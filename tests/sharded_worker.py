@@ -43,6 +43,8 @@ def main():
                                use_graph=use_graph)
             ns = mg.n_sharded_levels()
             assert ns >= 2, ns
+            # the sharded levels run as fused legs on the rank's window (block + ghost rows)
+            assert all(mg.fused_legs(l) for l in range(ns)), [mg.fused_legs(l) for l in range(L - 1)]
             want_mode = os.environ.get("AMGB_HALO", "peer")
             assert mg.halo_mode() == want_mode, (mg.halo_mode(), want_mode)
             single = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1)

@@ -405,6 +405,28 @@ def test_fused_legs_cycle_is_bit_identical(n, L, eps, nu, fuse):
         assert legs.launches_per_vcycle() < plain.launches_per_vcycle()
 
 
+@pytest.mark.parametrize("n,L,eps,nu", [(35, 8, 1.0, 2), (35, 7, 1.0, 1), (64, 9, 1.0, 3), (100, 11, 1.0, 2),
+                                        (129, 12, 1e-3, 2), (257, 14, 1.0, 2)])
+def test_coarse_tail_is_bit_identical(n, L, eps, nu):
+    """The small levels + coarsest solve in ONE launch (fuse bit 4) against the per-operator
+    kernels and the oracle, every level, bit for bit; and on its own as well as combined with
+    the streaming legs."""
+    sm = amg.DampedJacobi(2.0 / 3.0, nu)
+    tail, mo, _ = make_pair(n, L, sm, eps, fuse=16)
+    both, _, _ = make_pair(n, L, sm, eps, fuse=1 | 4 | 16)
+    plain, _, _ = make_pair(n, L, sm, eps, fuse=0)
+    assert 1 <= tail.tail_first() < L - 1
+    assert plain.tail_first() == -1
+    for _ in range(3):
+        tail.vcycle(); both.vcycle(); plain.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert tail.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert both.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert plain.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert tail.get_rhs(l).tobytes() == mo.f(l).tobytes(), l
+    assert tail.launches_per_vcycle() < plain.launches_per_vcycle()
+
+
 def test_fused_legs_small_tiles(monkeypatch):
     """Force narrow strips / short line chunks so one level is cut into many tiles."""
     monkeypatch.setenv("AMGB_LEG_W", "37")
