@@ -321,7 +321,7 @@ struct Operator {
     bool has_diag = false;
     for (int d = 0; d < D.n_diag; ++d) has_diag |= (D.off[d] == 0);
     if (!has_diag) return;
-    int B = 1024, max_far = 0;
+    int B = 992, max_far = 0;  // 31 compute warps + the producer warp
     std::vector<int> dists[2];
     for (int side = 0; side < 2; ++side) {  // 0: forward (updated = lower), 1: backward (updated = upper)
       // ascending column order of the already-updated side: forward = most negative offset
@@ -434,7 +434,7 @@ struct Operator {
       CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       attr_done = true;
     }
-    LAUNCH(kern, 1, lines_T, lines_smem, s, L, g, u);
+    LAUNCH(kern, 1, lines_T + 32, lines_smem, s, L, g, u);  // + the producer warp
   }
 
   void ensure_colors(cudaStream_t s) {

@@ -374,26 +374,30 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
   double* wp = wq + 32;                 // 32 warp totals (p)
   uint64_t* bars = reinterpret_cast<uint64_t*>(wp + 32);  // STAGES mbarriers (8 slots reserved)
   double* stage = wp + 32 + 8;          // STAGES x (3 + n_far) x B
-  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
+  // The last warp of the block is the PRODUCER: its lane 0 issues the TMA copies STAGES-1 steps
+  // ahead and waits for the next step's stage, off the critical path of the compute warps.
+  const int T = blockDim.x - 32, t = threadIdx.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
+  const bool producer = (t >= T);
   const int n = D.n, B = D.B, n_arr = 3 + D.n_far;
   const int n_steps = (n + B - 1) / B;
 
-  if (t == 0) {
+  if (t == T) {
     for (int i = 0; i < STAGES; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // positions before the start of the sweep are read with a zero coefficient: keep them finite
-  for (int i = t; i <= D.ring_mask; i += T) ring[i] = 0.0;
+  for (int i = t; i <= D.ring_mask; i += blockDim.x) ring[i] = 0.0;
   __syncthreads();
 
-  auto issue = [&](int step) {  // thread 0 only
+  auto issue = [&](int step) {  // producer lane 0 only
     if (step >= n_steps) return;
     const int b0 = step * B;
     const int cnt = min(B, n - b0);
     const uint32_t bytes = (uint32_t)((cnt + 1) & ~1) * 8u;  // arrays are padded, b0 is even
     const int sidx = step % STAGES;
     double* dst = stage + (size_t)sidx * n_arr * B;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the stage buffer was last READ before the block barrier that ended the previous step; a
+    // write-after-read across proxies needs only that ordering
     mbar_expect_tx(&bars[sidx], bytes * (uint32_t)n_arr);
     tma_load_1d(dst, g + b0, bytes, &bars[sidx]);
     tma_load_1d(dst + B, D.dinv + b0, bytes, &bars[sidx]);
@@ -401,8 +405,11 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
     for (int k = 0; k < D.n_far; ++k)
       tma_load_1d(dst + (3 + k) * B, D.far + (size_t)k * D.np + b0, bytes, &bars[sidx]);
   };
-  if (t == 0)
+  if (t == T) {
     for (int st = 0; st < STAGES - 1; ++st) issue(st);
+    mbar_wait(&bars[0], 0u);
+  }
+  __syncthreads();  // stage 0 has landed
 
   const int stage_stride = n_arr * B;
   const int i0 = t * R;  // first row of this thread inside the block
@@ -410,10 +417,28 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
   double* const u0 = (D.dir > 0) ? u + i0 : u + (n - 1 - i0);
   const int ustep = (D.dir > 0) ? 1 : -1;
   int sidx = 0, phase = 0;
-  if (t == 0) mbar_wait(&bars[0], 0u);
-  __syncthreads();  // stage 0 has landed
   for (int step = 0; step < n_steps; ++step) {
-    if (t == 0) issue(step + STAGES - 1);  // its buffer was released by the barrier ending step-1
+    int nsidx = sidx + 1, nphase = phase;
+    if (nsidx == STAGES) {
+      nsidx = 0;
+      nphase ^= 1;
+    }
+    if (producer) {
+      if (t == T) {
+        issue(step + STAGES - 1);  // its buffer was released by the barrier ending step-1
+        if (step + 1 < n_steps) mbar_wait(&bars[nsidx], (uint32_t)nphase);  // next step's stage has landed
+      }
+      if (!D.short_carry && n_warps > 1) {  // stay in step with the compute warps' barriers
+        __syncthreads();
+        __syncthreads();
+      } else if (n_warps > 1) {
+        __syncthreads();
+      }
+      __syncthreads();
+      sidx = nsidx;
+      phase = nphase;
+      continue;
+    }
     const int b0 = step * B;
     const double* src = stage + sidx * stage_stride + i0;
     Affine rows[R];
@@ -482,12 +507,8 @@ __global__ void __launch_bounds__(1024) k_gs_lines(GsLineDesc D, const double* _
         u0[(long long)ustep * (b0 + r)] = x;
       }
     }
-    if (++sidx == STAGES) {
-      sidx = 0;
-      phase ^= 1;
-    }
-    // thread 0 makes sure the next step's stage has landed before everyone passes the barrier
-    if (t == 0 && step + 1 < n_steps) mbar_wait(&bars[sidx], (uint32_t)phase);
+    sidx = nsidx;
+    phase = nphase;
     __syncthreads();  // ring complete, this step's stage buffer free, next stage visible
   }
 }
