@@ -105,6 +105,7 @@ SIGNATURES = {
     "amgb_hierarchy_rss": (_i, [_p, C.POINTER(_d)]),
     "amgb_solve": (_i, [_p, C.POINTER(_l), C.POINTER(_d)]),
     "amgb_solve_relative": (_i, [_p, _d, C.POINTER(_l), C.POINTER(_d)]),
+    "amgb_solve_pcg": (_i, [_p, _d, _l, C.POINTER(_l), C.POINTER(_d)]),
     "amgb_hierarchy_iters_done": (_l, [_p]),
     "amgb_hierarchy_error_history": (_l, [_p, _pd, _l]),
     "amgb_synchronize": (_i, [_p]),
@@ -504,6 +505,13 @@ class Multigrid:
     def solve_relative(self, rel_tol):
         it, rel = _l(), _d()
         _check(lib().amgb_solve_relative(self.h, rel_tol, C.byref(it), C.byref(rel)))
+        self.iters_done, self.last_error = it.value, rel.value
+        return self.get_soln(0)
+
+    def solve_pcg(self, rel_tol, max_iters=1000):
+        """Conjugate gradients preconditioned by one V-cycle (beyond the reference)."""
+        it, rel = _l(), _d()
+        _check(lib().amgb_solve_pcg(self.h, rel_tol, max_iters, C.byref(it), C.byref(rel)))
         self.iters_done, self.last_error = it.value, rel.value
         return self.get_soln(0)
 

@@ -667,6 +667,7 @@ struct amgb_hierarchy {
   // second stream: the halo exchange of a sweep runs beside the sweep of the block interior
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_leg;  // per sharded level: the side-stream exchange of the down leg's result
   bool overlap = true;
 
   ~amgb_hierarchy() {
@@ -675,6 +676,7 @@ struct amgb_hierarchy {
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    for (cudaEvent_t e : ev_leg) cudaEventDestroy(e);
     if (aux_stream) cudaStreamDestroy(aux_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
@@ -688,6 +690,8 @@ struct amgb_hierarchy {
     CUDA_CHECK(cudaStreamCreateWithPriority(&aux_stream, cudaStreamNonBlocking, prio_hi));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    ev_leg.assign(n_sharded, nullptr);
+    for (cudaEvent_t& e : ev_leg) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const char* ov = std::getenv("AMGB_OVERLAP");
     overlap = !(ov && std::string(ov) == "0");
     const char* env = std::getenv("AMGB_HALO");
@@ -1010,6 +1014,20 @@ struct amgb_hierarchy {
   // stream capture) and report the resident warps per SM the register count allows.
   template <int KIND, unsigned MASK>
   static void sleg_do(const sleg::Params& P, cudaStream_t s, int action, int* warps_per_sm) {
+    // five-point up leg: three lines in flight at 12 warps/SM measured 6 % faster than two at 16
+    if (MASK == sleg::kMask5 && env_int("AMGB_SLEG_PF", KIND == sleg::UP ? 3 : 2) == 3) {
+      auto kern3 = sleg::k_stream_leg<KIND, MASK, 2, 3>;
+      if (action == 1) {
+        LAUNCH(kern3, (P.n_warps + 3) / 4, 128, 0, s, P);
+      } else if (action == 2) {
+        cudaFuncAttributes fa{};
+        CUDA_CHECK(cudaFuncGetAttributes(&fa, kern3));
+        if (warps_per_sm) *warps_per_sm = std::max(1, 65536 / (std::max(fa.numRegs, 1) * 128)) * 4;
+        CUDA_CHECK(cudaFuncSetAttribute(kern3, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxL1));
+      }
+      return;
+    }
     auto kern = sleg::k_stream_leg<KIND, MASK, 2>;
     if (action == 1) {
       LAUNCH(kern, (P.n_warps + 3) / 4, 128, 0, s, P);
@@ -1056,6 +1074,7 @@ struct amgb_hierarchy {
   //   fuse bit 3: TMA-ring legs for the other banded levels
   void prepare_legs(int l) {
     if ((int)legs.size() != L) legs.assign(L, LegLevel());
+    if ((int)leg_side.size() != L) leg_side.assign(L, 0);
     LegLevel& G = legs[l];
     G.ok = false;
     if (!(opt.fuse & 12) || opt.smoother != AMGB_SMOOTHER_JACOBI || opt.smoother_iters < 1 || l + 1 >= L) return;
@@ -1215,6 +1234,7 @@ struct amgb_hierarchy {
     G.ok = true;
   }
   bool leg_ok(int l) const { return l >= 0 && l < (int)legs.size() && legs[l].ok; }
+  std::vector<char> leg_side;  // per level: this cycle's down-leg result exchange went to the side stream
 
   // ---- coarse tail (k_coarse_tail): levels [tail_first, L) of a damped-Jacobi cycle in one launch
   int tail_first = -1;
@@ -1285,6 +1305,15 @@ struct amgb_hierarchy {
           // ghost rows of the leg's input: the iterate on level 0, the right-hand side below
           exchange(l, l == 0 ? lv[l].u.p : lv[l].fw.p, s);
           leg_down(l, s);
+          // The up leg needs the ghost rows of this result: exchange them now on the side stream,
+          // while the coarser levels run, instead of on the way back up.
+          leg_side[l] = p2p && overlap && aux_stream && l < (int)ev_leg.size();  // (NCCL calls stay on one stream)
+          if (leg_side[l]) {
+            CUDA_CHECK(cudaEventRecord(ev_fork, s));
+            CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+            exchange(l, lv[l].tmp.p, aux_stream);
+            CUDA_CHECK(cudaEventRecord(ev_leg[l], aux_stream));
+          }
           if (!lv[l + 1].sharded)  // first agglomerated level: every rank gets the whole right-hand side
             allgather_blocks(lv[l + 1].f.p, coarse_block_start, s);
         } else {
@@ -1304,7 +1333,8 @@ struct amgb_hierarchy {
     for (int l = std::min(lt, L - 1) - 1; l >= 0; --l) {
       if (leg_ok(l)) {  // tmp_l + P u_{l+1}, sweeps -> u_l
         if (lv[l].sharded) {
-          exchange(l, lv[l].tmp.p, s);
+          if (leg_side[l]) CUDA_CHECK(cudaStreamWaitEvent(s, ev_leg[l], 0));
+          else exchange(l, lv[l].tmp.p, s);
           if (lv[l + 1].sharded) exchange(l + 1, lv[l + 1].u.p, s);
         }
         leg_up(l, s);
@@ -2050,6 +2080,67 @@ int amgb_solve_relative(amgb_hierarchy* h, double rel_tol, int64_t* iters_done, 
     h->iters_done = iter;
     if (iters_done) *iters_done = iter;
     if (last_rel) *last_rel = rel;
+  });
+}
+// Conjugate gradients on A u = b preconditioned by one V-cycle from a zero guess (z = V(r)).
+// The signs of a negative definite A (the reference's Laplacian, grid.hpp:62) cancel in
+// alpha = (r.z) / (p.Ap) and beta, so the plain recurrences apply.  Needs a symmetric cycle
+// (damped Jacobi or multicolour GS with equal pre- and post-smoothing, symmetric GS).
+int amgb_solve_pcg(amgb_hierarchy* h, double rel_tol, int64_t max_iters, int64_t* iters_done,
+                   double* last_rel_residual) {
+  return guarded([&] {
+    if (!h) throw std::invalid_argument("null argument");
+    if (h->lv[0].sharded) throw ApiError(AMGB_ESTATE, "amgb_solve_pcg runs on a single GPU");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    LevelState& S = h->lv[0];
+    const int N = (int)h->n[0];
+    const size_t bytes = sizeof(double) * (size_t)N;
+    const int nb = std::max(1, blocks_for(N, 256));
+    DevBuf<double> b, x, r, p, q, zero;
+    for (DevBuf<double>* v : {&b, &x, &r, &p, &q, &zero}) v->alloc((size_t)N + 8);
+    zero.zero(s);
+    CUDA_CHECK(cudaMemcpyAsync(b.p, S.f.p, bytes, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(x.p, S.u.p, bytes, cudaMemcpyDeviceToDevice, s));
+    auto dot = [&](const double* a_, const double* b_) {
+      LAUNCH(dev::k_dot_partial, nb, 256, 0, s, a_, b_, N, h->partial.p);
+      LAUNCH(dev::k_sum_partials, 1, 256, 0, s, h->partial.p, nb, h->scalar.p);
+      return h->finish_scalar_local();
+    };
+    h->ops[0]->residual(x.p, b.p, r.p, s);  // r = b - A x
+    const double bnorm2 = dot(b.p, b.p);
+    double rr = dot(r.p, r.p);
+    double rel = bnorm2 > 0.0 ? std::sqrt(rr / bnorm2) : 0.0;
+    h->history.clear();
+    int64_t iter = 0;
+    double rz_old = 0.0;
+    while (iter < max_iters && rel > rel_tol) {
+      // z = V(r): one cycle on A z = r from z = 0
+      CUDA_CHECK(cudaMemcpyAsync(S.f.p, r.p, bytes, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaMemsetAsync(S.u.p, 0, bytes, s));
+      h->vcycle();
+      const double* z = S.u.p;
+      const double rz = dot(r.p, z);
+      if (iter == 0) CUDA_CHECK(cudaMemcpyAsync(p.p, z, bytes, cudaMemcpyDeviceToDevice, s));
+      else LAUNCH(dev::k_xpay, nb, 256, 0, s, p.p, z, rz / rz_old, N);
+      h->ops[0]->residual(p.p, zero.p, q.p, s);  // q = 0 - A p
+      const double pq = dot(p.p, q.p);           // = -(p . A p)
+      if (pq == 0.0 || !std::isfinite(pq)) break;
+      const double alpha = -rz / pq;
+      LAUNCH(dev::k_axpy, nb, 256, 0, s, x.p, alpha, p.p, N);
+      LAUNCH(dev::k_axpy, nb, 256, 0, s, r.p, alpha, q.p, N);  // r -= alpha A p
+      rz_old = rz;
+      rr = dot(r.p, r.p);
+      rel = std::sqrt(rr / bnorm2);
+      h->history.push_back(rel);
+      iter += 1;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(S.f.p, b.p, bytes, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(S.u.p, x.p, bytes, cudaMemcpyDeviceToDevice, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    h->iters_done = iter;
+    if (iters_done) *iters_done = iter;
+    if (last_rel_residual) *last_rel_residual = rel;
   });
 }
 int64_t amgb_hierarchy_iters_done(const amgb_hierarchy* h) { return h ? h->iters_done : 0; }

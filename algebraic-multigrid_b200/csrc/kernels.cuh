@@ -677,6 +677,28 @@ __global__ void __launch_bounds__(256) k_sumsq_partial(const double* __restrict_
   if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 
+// ------------------------------------------------------------------ vector kernels of the PCG wrapper
+// (the V-cycle as the preconditioner of conjugate gradients)
+__global__ void __launch_bounds__(256) k_dot_partial(const double* __restrict__ x, const double* __restrict__ y,
+                                                     int n, double* __restrict__ partial) {
+  __shared__ double sh[32];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const double v = (t < n) ? x[t] * y[t] : 0.0;
+  const double tot = block_sum_256(v, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+// y += a x
+__global__ void __launch_bounds__(256) k_axpy(double* __restrict__ y, double a, const double* __restrict__ x, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) y[t] = y[t] + a * x[t];
+}
+// p = z + beta p
+__global__ void __launch_bounds__(256) k_xpay(double* __restrict__ p, const double* __restrict__ z, double beta,
+                                              int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = z[t] + beta * p[t];
+}
+
 // ------------------------------------------------------------------ coarsest solve
 // x = (L D L^T)^{-1} f with the banded factor of host_setup.hpp, right-looking
 // substitutions (multigrid.hpp:287-288).  One block; the vector lives in shared

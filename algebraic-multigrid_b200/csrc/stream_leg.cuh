@@ -77,13 +77,13 @@ __host__ __device__ constexpr int popc9(unsigned v) {
   return c;
 }
 
-template <int KIND, unsigned MASK, int NU>
+template <int KIND, unsigned MASK, int NU, int PF_ = 2>
 struct Leg {
   static constexpr int ND = popc9(MASK);
   static constexpr int NS = (KIND == DOWN_U) ? NU + 1 : NU;  // chained stencil stages
   static constexpr int X = (KIND == UP) ? 0 : 1;
   static constexpr int H = NS + X;                           // lanes lost on each side
-  static constexpr int PF = 2;                               // lines in flight
+  static constexpr int PF = PF_;                             // lines in flight
   static constexpr int RS = NS + 1 + PF;                     // register-ring slots
   static constexpr int DC = popc9(MASK & 0xFu);              // rank of the centre slot (0,0)
   static constexpr int S_OUT = (KIND == UP) ? NS : NS - 1;   // stage whose result is the iterate
@@ -251,9 +251,10 @@ struct Leg {
   }
 };
 
-template <int KIND, unsigned MASK, int NU>
-__global__ void __launch_bounds__(128, (popc9(MASK) <= 5 ? 4 : 3)) k_stream_leg(const __grid_constant__ Params P) {
-  Leg<KIND, MASK, NU>::run(P);
+template <int KIND, unsigned MASK, int NU, int PF_ = 2>
+__global__ void __launch_bounds__(128, ((popc9(MASK) <= 5 && PF_ == 2) ? 4 : 3))
+    k_stream_leg(const __grid_constant__ Params P) {
+  Leg<KIND, MASK, NU, PF_>::run(P);
 }
 
 }  // namespace sleg

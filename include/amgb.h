@@ -237,6 +237,14 @@ int amgb_solve(amgb_hierarchy* h, int64_t* iters_done, double* last_error);
  * checked every compute_error_every_n_iters cycles, capped at n_iters */
 int amgb_solve_relative(amgb_hierarchy* h, double rel_tol, int64_t* iters_done,
                         double* last_rel_residual);
+/* Beyond the reference (README.md:127 of the reference names it as
+ * the usual use): conjugate gradients on A u = b preconditioned by one V-cycle from a zero guess,
+ * starting from the stored level-0 solution; stops when ||r||_2 / ||b||_2 <= rel_tol or after
+ * max_iters iterations.  The residual history is kept like amgb_solve's.  Single GPU; the cycle
+ * must be symmetric (damped Jacobi / multicolour GS / symmetric GS with equal pre- and
+ * post-smoothing, which is how every cycle of this library is built). */
+int amgb_solve_pcg(amgb_hierarchy* h, double rel_tol, int64_t max_iters, int64_t* iters_done,
+                   double* last_rel_residual);
 int64_t amgb_hierarchy_iters_done(const amgb_hierarchy* h);
 /* copies min(cap, n) history entries, returns n */
 int64_t amgb_hierarchy_error_history(const amgb_hierarchy* h, double* out, int64_t cap);
