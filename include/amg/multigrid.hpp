@@ -145,6 +145,16 @@ class Multigrid {
     if (n) amgb_hierarchy_error_history(h, out.data(), n);
     return out;
   }
+  // Conjugate gradients preconditioned by one V-cycle (the use the reference's README names,
+  // README.md:127); stops at ||r||_2 / ||b||_2 <= rel_tol or after max_iters iterations.
+  const VectorT<EleType>& solve_pcg(EleType rel_tol, size_t max_iters = 1000) {
+    int64_t it = 0;
+    double rel = 0;
+    detail::check(amgb_solve_pcg(h, rel_tol, (int64_t)max_iters, &it, &rel));
+    iters_done_ = (size_t)it;
+    last_error_ = rel;
+    return get_soln(0);
+  }
   amgb_hierarchy* handle() { return h; }
 };
 
