@@ -164,5 +164,9 @@ def test_plan_shape_for_the_bench_config():
             blocks = np.diff(starts[l])
             assert blocks.min() > 0 and blocks.max() - blocks.min() <= 2 ** ns + sizes[l] % world + 1
             assert (starts[l][:-1] % 2 == 0).all()
+            # ghost rows for the fused legs: three chained stencil stages + the restriction's
+            # neighbours (3 w + 4), on both sides, and every block at least as long as what it sends
+            assert lo[l] >= 3 * bw[l] + 4 and hi[l] >= 3 * bw[l] + 4 + gh[l]
+            assert blocks.min() >= max(lo[l], hi[l])
     ns1, *_ = amg.partition_plan(sizes, bw, 1, 1 << 18)
     assert ns1 == 0
