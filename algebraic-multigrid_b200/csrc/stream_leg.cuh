@@ -163,6 +163,22 @@ struct Leg {
     Line R[RS];
     double w[NS][3];  // w[s]: results of stage s (0 = input) on its last three lines
   };
+  // The three-line windows rotate with the step.  When the ring period RS is a multiple of 3 the
+  // slot of a line is a compile-time function of the step's position P_ in the unrolled period
+  // (newest P_ % 3) and nothing moves; otherwise the window is shifted.
+  static constexpr bool kStaticWindows = (RS % 3 == 0);
+  static __device__ __forceinline__ constexpr int WP(int p) { return kStaticWindows ? p % 3 : 2; }        // line j + 1
+  static __device__ __forceinline__ constexpr int W0(int p) { return kStaticWindows ? (p + 2) % 3 : 1; }  // line j
+  static __device__ __forceinline__ constexpr int WM(int p) { return kStaticWindows ? (p + 1) % 3 : 0; }  // line j - 1
+  static __device__ __forceinline__ void push(double (&w)[3], double v, int p) {
+    if (kStaticWindows) {
+      w[p % 3] = v;
+    } else {
+      w[0] = w[1];
+      w[1] = w[2];
+      w[2] = v;
+    }
+  }
 
   // One step: loads of line jj + 1 + PF, input stage on line jj + 1 (ring slot P_), stage s on
   // line jj - s + 1 (slot P_ - s), restriction of the residual line.  g1 = first row of line jj + 1.
@@ -177,9 +193,7 @@ struct Leg {
       const Line& L = S.R[P_ % RS];
       const int k = g1 + lane;
       const double in = input(L, P, k + P.base);
-      S.w[0][0] = S.w[0][1];
-      S.w[0][1] = S.w[0][2];
-      S.w[0][2] = in;
+      push(S.w[0], in, P_);
       if (S_OUT == 0 && own_lane && jj + 1 >= j0 && jj + 1 < j1 && k >= P.own_begin && k < P.own_end) P.uout[k] = in;
     }
 #pragma unroll
@@ -187,7 +201,7 @@ struct Leg {
       const Line& L = S.R[(P_ - s + 2 * RS) % RS];
       const int j = jj - s + 1;
       const int k = g1 - s * m + lane;
-      const double acc = stencil(L, S.w[s - 1][0], S.w[s - 1][1], S.w[s - 1][2]);
+      const double acc = stencil(L, S.w[s - 1][WM(P_)], S.w[s - 1][W0(P_)], S.w[s - 1][WP(P_)]);
       const bool own = own_lane && j >= j0 && j < j1 && k >= P.own_begin && k < P.own_end;
       if (KIND != UP && s == NS) {
         // residual -> restriction: f_c[J] = (.5 r[2J] + r[2J+1]) + .5 r[2J+2]   (interpolator.hpp:64-68)
@@ -200,13 +214,9 @@ struct Leg {
         }
       } else {
         const double diag = L.a[DC];
-        const double xc = S.w[s - 1][1];
+        const double xc = S.w[s - 1][W0(P_)];
         const double out = (diag == 0.0) ? xc : __dadd_rn(xc, __dmul_rn(P.omega, __ddiv_rn(acc, diag)));
-        if (s < NS) {
-          S.w[s][0] = S.w[s][1];
-          S.w[s][1] = S.w[s][2];
-          S.w[s][2] = out;
-        }
+        if (s < NS) push(S.w[s], out, P_);
         if (s == S_OUT && own) P.uout[k] = out;
       }
     }

@@ -79,9 +79,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples that arrived in [t0, t1] (the timed
+        region); nvidia-smi is started long before it because it needs about a second to come up."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,7 +93,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if t0 is None or t0 <= r[0] <= t1 + 0.05]
+        window = "timed region"
+        if not rows:   # region shorter than the sampling period: the samples of the whole run
+            rows, window = [r[1:] for r in self.rows], "whole run (no sample fell into the timed region)"
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -102,7 +108,7 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_hbm_peak():
@@ -197,6 +203,7 @@ def run_b200(a):
     levels = a.levels or default_levels(a.n)
     smoother = {"jacobi": amg.DampedJacobi(2.0 / 3.0, 2), "color": amg.MulticolorGaussSeidel(1),
                 "gs": amg.SparseGaussSeidel()}[a.smoother]
+    sampler = ClockSampler(local) if rank == 0 else None   # running well before the timed region
     t0 = time.perf_counter()
     A = amg.Grid.laplacian(a.n, a.eps)
     b = amg.Grid.rhs(a.n)
@@ -214,20 +221,21 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     # ---- device-resident V-cycles (value) ----
-    sampler = ClockSampler(local) if rank == 0 else None   # samples warm-up + timed region
     for _ in range(a.warmup):
         mg.vcycle()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = amg.kernel_launches()
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(a.steps):
         mg.vcycle()
     e1.record(stream)
     barrier()
+    tw1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = amg.kernel_launches() - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(tw0, tw1) if sampler else None
     if dist is not None:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
