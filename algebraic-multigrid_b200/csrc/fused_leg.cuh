@@ -113,10 +113,6 @@ AMGB_LEG_FN double prolong_entry(const double* e, int e_first, int n_coarse, lon
   return acc;
 }
 
-struct Win {
-  int alo, ahi;  // 16-byte aligned row window [alo, ahi) the TMA copies; empty when alo == ahi
-};
-
 // One tile.  env.phase(fn) runs fn(t) for all threads t and ends with a block barrier.
 //
 // Schedule: ONE phase per step.  At step jj the input stage handles line jj + 2, stencil stage

@@ -476,68 +476,4 @@ Schedule gs_schedule(const Csc& M, bool forward) {
   return S;
 }
 
-// ------------------------------------------------------------------ band analysis
-
-BandStructure analyze_band(const Csc& M) {
-  BandStructure B;
-  const int n = M.cols;
-  if (M.rows != n) {
-    B.why = "not square";
-    return B;
-  }
-  // histogram of |row - col| over non-zero off-diagonal entries
-  int max_off = 0;
-  for (int c = 0; c < n; ++c)
-    for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p)
-      if (M.val[p] != 0.0) max_off = std::max(max_off, std::abs(M.rowidx[p] - c));
-  std::vector<char> seen((size_t)max_off + 1, 0);
-  for (int c = 0; c < n; ++c)
-    for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p)
-      if (M.val[p] != 0.0) seen[std::abs(M.rowidx[p] - c)] = 1;
-  std::vector<int> offs;
-  for (int d = 1; d <= max_off; ++d)
-    if (seen[d]) offs.push_back(d);
-  // near cluster: consecutive small offsets 1..q; far cluster: the rest, must be contiguous-ish
-  size_t t = 0;
-  int q = 0;
-  while (t < offs.size() && offs[t] == q + 1 && q < 2) {
-    q = offs[t];
-    ++t;
-  }
-  B.near = q;
-  if (t < offs.size()) {
-    B.far_lo = offs[t];
-    B.far_hi = offs.back();
-    if (B.far_hi - B.far_lo > 3) {
-      B.why = "far offsets spread over more than 4 diagonals";
-      return B;
-    }
-    if (B.far_lo <= 2 * (B.near + 2)) {
-      B.why = "far cluster too close to the diagonal";
-      return B;
-    }
-  }
-  for (int c = 0; c < n; ++c) {
-    double dia = 0.0, lo = 0.0, up = 0.0, nearlo = 0.0;
-    for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p) {
-      const int r = M.rowidx[p];
-      const double a = std::fabs(M.val[p]);
-      if (r == c) dia = a;
-      else if (r < c) {
-        lo += a;
-        if (c - r <= B.near) nearlo += a;
-      } else up += a;
-    }
-    if (dia == 0.0) {
-      B.why = "zero diagonal";
-      return B;
-    }
-    B.rho_lower = std::max(B.rho_lower, lo / dia);
-    B.rho_upper = std::max(B.rho_upper, up / dia);
-    B.alpha_near = std::max(B.alpha_near, nearlo / dia);
-  }
-  B.ok = true;
-  return B;
-}
-
 }  // namespace amgb

@@ -132,18 +132,4 @@ struct Schedule {
 };
 Schedule gs_schedule(const Csc& M, bool forward);
 
-// ---- banded-stencil structure of an operator (for the systolic GS kernel) ----
-// Offsets d = row - col of non-zero entries, split into "near" (|d| <= q) and
-// one "far" cluster [far_lo, far_hi] (by symmetry also the negative one).
-struct BandStructure {
-  bool ok = false;
-  int near = 0;              // max |d| of the near cluster (0 = diagonal only)
-  int far_lo = 0, far_hi = 0;  // far cluster, 0/0 when absent
-  double rho_lower = 0.0;    // max_k sum_{j<k} |a_kj| / |a_kk|
-  double rho_upper = 0.0;
-  double alpha_near = 0.0;   // max_k sum_{0<k-j<=near} |a_kj| / |a_kk|
-  std::string why;           // reason when !ok
-};
-BandStructure analyze_band(const Csc& M);
-
 }  // namespace amgb
