@@ -61,7 +61,7 @@ def workload_name(a):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -78,8 +78,14 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
+            cells = [c.strip() for c in line.split(",")]
+            try:   # nvidia-smi's own wall-clock stamp (the pipe may deliver lines late)
+                at = datetime.datetime.strptime(cells[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except (ValueError, IndexError):
+                at = time.time()
+            self.rows.append([at] + cells[1:])
 
     def stop(self, t0=None, t1=None):
         """Median SM clock / throttle reasons of the samples that arrived in [t0, t1] (the timed
@@ -226,13 +232,13 @@ def run_b200(a):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = amg.kernel_launches()
-    tw0 = time.perf_counter()
+    tw0 = time.time()
     e0.record(stream)
     for _ in range(a.steps):
         mg.vcycle()
     e1.record(stream)
     barrier()
-    tw1 = time.perf_counter()
+    tw1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = amg.kernel_launches() - launches0
     clocks = sampler.stop(tw0, tw1) if sampler else None
