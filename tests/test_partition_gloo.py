@@ -170,3 +170,48 @@ def test_plan_shape_for_the_bench_config():
             assert blocks.min() >= max(lo[l], hi[l])
     ns1, *_ = amg.partition_plan(sizes, bw, 1, 1 << 18)
     assert ns1 == 0
+
+
+def _window_leg_down(M, f, u, nu, lo, hi):
+    """The fused down leg as a rank sees it: only rows [lo, hi) of the operator, f and u exist
+    (everything else contributes zeros, like the kernel's out-of-window lanes); returns the
+    smoothed iterate and the residual on the window."""
+    n = M.shape[0]
+    W = M[lo:hi, lo:hi].tocsr()
+    d = W.diagonal()
+    uw, fw = u[lo:hi].copy(), f[lo:hi]
+    for _ in range(nu):
+        r = fw - W @ uw
+        uw = uw + OMEGA * (r / d)
+    return uw, fw - W @ uw
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_ghost_rows_cover_the_fused_legs(world):
+    """The plan's ghost rows are wide enough: a leg computed on a rank's window (block + ghost
+    rows, nothing else) gives, on the OWNED rows, what the leg on the whole level gives -- two
+    sweeps + residual for the down leg (and its restriction), prolongation + two sweeps for the
+    up leg.  Same floating-point operation count per row, so the comparison is to rounding
+    (the CUDA kernels are compared bit for bit on the GPU, tests/sharded_worker.py)."""
+    n = 129
+    Ao, b = O.laplacian(n), O.rhs(n)
+    sizes = O.level_sizes(n * n, 8)
+    mo = O.Multigrid(Ao, b, 8, 1e-9, 1, 1, O.SMOOTHER_JACOBI, SWEEPS, OMEGA)
+    mats = [mo.A(l).to_scipy().tocsr() for l in range(8)]
+    bw = half_bandwidths(mats)
+    ns, starts, hlo, hhi, ghost = amg.partition_plan(sizes, bw, world, 500)
+    assert ns >= 2
+    rng = np.random.default_rng(5)
+    for l in range(ns):
+        M, N = mats[l], sizes[l]
+        f, u = rng.standard_normal(N), rng.standard_normal(N)
+        # whole-level reference
+        uw, rw = _window_leg_down(M, f, u, SWEEPS, 0, N)
+        for g in range(world):
+            s, e = int(starts[l][g]), int(starts[l][g + 1])
+            lo, hi = max(0, s - int(hlo[l])), min(N, e + int(hhi[l]))
+            ug, rg = _window_leg_down(M, f, u, SWEEPS, lo, hi)
+            np.testing.assert_allclose(ug[s - lo:e - lo], uw[s:e], rtol=0, atol=1e-13 * np.abs(uw).max())
+            # residual on the owned rows and one row either side (the restriction reads r[k-1], r[k+1])
+            a, z = max(s - 1, 0), min(e + 1, N)
+            np.testing.assert_allclose(rg[a - lo:z - lo], rw[a:z], rtol=0, atol=1e-12 * np.abs(rw).max())
