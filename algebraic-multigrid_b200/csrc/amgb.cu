@@ -1014,8 +1014,13 @@ struct amgb_hierarchy {
   // stream capture) and report the resident warps per SM the register count allows.
   template <int KIND, unsigned MASK>
   static void sleg_do(const sleg::Params& P, cudaStream_t s, int action, int* warps_per_sm) {
+    if (P.nu == 1) sleg_do_nu<KIND, MASK, 1>(P, s, action, warps_per_sm);
+    else sleg_do_nu<KIND, MASK, 2>(P, s, action, warps_per_sm);
+  }
+  template <int KIND, unsigned MASK, int NU>
+  static void sleg_do_nu(const sleg::Params& P, cudaStream_t s, int action, int* warps_per_sm) {
     // five-point up leg: three lines in flight at 12 warps/SM measured 6 % faster than two at 16
-    if (MASK == sleg::kMask5 && env_int("AMGB_SLEG_PF", KIND == sleg::UP ? 3 : 2) == 3) {
+    if (NU == 2 && MASK == sleg::kMask5 && env_int("AMGB_SLEG_PF", KIND == sleg::UP ? 3 : 2) == 3) {
       auto kern3 = sleg::k_stream_leg<KIND, MASK, 2, 3>;
       if (action == 1) {
         LAUNCH(kern3, (P.n_warps + 3) / 4, 128, 0, s, P);
@@ -1028,7 +1033,7 @@ struct amgb_hierarchy {
       }
       return;
     }
-    auto kern = sleg::k_stream_leg<KIND, MASK, 2>;
+    auto kern = sleg::k_stream_leg<KIND, MASK, NU>;
     if (action == 1) {
       LAUNCH(kern, (P.n_warps + 3) / 4, 128, 0, s, P);
     } else if (action == 2) {
@@ -1070,7 +1075,7 @@ struct amgb_hierarchy {
   }
   // Plan the fused legs of level l (whole levels of a damped-Jacobi cycle with a banded DIA
   // operator); levels the plan does not cover keep the per-operator kernels.
-  //   fuse bit 2: register-streaming legs for 3 x 3 line stencils (two sweeps per smooth call)
+  //   fuse bit 2: register-streaming legs for 3 x 3 line stencils (one or two sweeps per smooth call)
   //   fuse bit 3: TMA-ring legs for the other banded levels
   void prepare_legs(int l) {
     if ((int)legs.size() != L) legs.assign(L, LegLevel());
@@ -1086,7 +1091,7 @@ struct amgb_hierarchy {
     if (S.sharded) {
       // row block + ghost rows: the streaming kernels run on the rank's window of the level
       const DevDia& W = ops[l]->win;
-      if (!(opt.fuse & 4) || nu != 2 || !W.val.p || W.n_diag > 10) return;
+      if (!(opt.fuse & 4) || (nu != 1 && nu != 2) || !W.val.p || W.n_diag > 10) return;
       leg::Plan st = leg::plan_leg(leg::UP, nu, (int)n[l], W.n_diag, ops[l]->win_off.data(), 148, 200 * 1024);
       if (!st.ok || !(st.P.m < st.P.n) || st.P.rho != 1) return;
       int wmax = 0;
@@ -1096,6 +1101,7 @@ struct amgb_hierarchy {
       unsigned mask = 0;
       for (int d = 0; d < W.n_diag; ++d) mask |= 1u << ((st.P.line_a[d] + 1) * 3 + st.P.delta[d] + 1);
       sleg::Params dummy{};
+      dummy.nu = nu;
       if (!sleg_dispatch(kind_down, mask, dummy, nullptr, 0) || !sleg_dispatch(sleg::UP, mask, dummy, nullptr, 0)) return;
       int n_sm = 148;
       CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -1105,6 +1111,7 @@ struct amgb_hierarchy {
         sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
         const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", wps);
         sleg::Params P{};
+        P.nu = nu;
         P.base = (int)(S.s - S.halo_lo);
         P.n_global = (int)n[l];
         P.own_begin = S.halo_lo;
@@ -1142,13 +1149,14 @@ struct amgb_hierarchy {
     }
     const DevMat& A = ops[l]->rows_of_A();
     if (!A.is_dia || A.dia.n_diag > 10 || A.dia.rows.p) return;
-    if ((opt.fuse & 4) && nu == 2) {
+    if ((opt.fuse & 4) && (nu == 1 || nu == 2)) {
       // line structure from the TMA-ring planner; the streaming kernels need rho == 1
       leg::Plan st = leg::plan_leg(leg::UP, nu, (int)n[l], A.dia.n_diag, A.dia.off, 148, 200 * 1024);
       if (st.ok && st.P.m < st.P.n && st.P.rho == 1) {
         unsigned mask = 0;
         for (int d = 0; d < A.dia.n_diag; ++d) mask |= 1u << ((st.P.line_a[d] + 1) * 3 + st.P.delta[d] + 1);
         sleg::Params dummy{};
+        dummy.nu = nu;
         if (sleg_dispatch(kind_down, mask, dummy, nullptr, 0) && sleg_dispatch(sleg::UP, mask, dummy, nullptr, 0)) {
           int n_sm = 148;
           CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
@@ -1157,6 +1165,7 @@ struct amgb_hierarchy {
             sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
             const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", wps);
             sleg::Params P{};
+            P.nu = nu;
             P.base = 0;
             P.n_global = (int)n[l];
             P.own_begin = 0;
@@ -1734,7 +1743,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
     // sharding (they run as streaming legs on the rank's window); the levels below, a few
     // hundred thousand rows at most, are agglomerated.
     int max_sharded = 1 << 30;
-    if ((o.fuse & 4) && o.smoother_iters == 2) {
+    if ((o.fuse & 4) && (o.smoother_iters == 1 || o.smoother_iters == 2)) {
       max_sharded = 0;
       for (int l = 0; l + 1 < L; ++l) {
         const Csc& M = mats[l];
@@ -1808,7 +1817,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
       S.fw.alloc(S.n_vec() + 8);
       S.fw.zero(s);
       // window mirror of the operator for the fused legs (block + ghost rows on both sides)
-      if ((o.fuse & 4) && o.smoother == AMGB_SMOOTHER_JACOBI && o.smoother_iters == 2)
+      if ((o.fuse & 4) && o.smoother == AMGB_SMOOTHER_JACOBI && (o.smoother_iters == 1 || o.smoother_iters == 2))
         h->ops[l]->build_window((int)(S.s - S.halo_lo), (int)S.n_vec(), s);
     }
     if (!(l + 1 == L && o.skip_dead_coarse_smooth)) h->prepare_smoother(l);

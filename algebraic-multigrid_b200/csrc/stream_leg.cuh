@@ -52,6 +52,7 @@ struct Params {
   int own_end;
   int cbase;      // global coarse index of fc[0] and e[0]
   int n_e;        // entries of e / fc that exist locally
+  int nu;         // Jacobi sweeps per smooth call (selects the kernel instantiation on the host)
   int n;         // rows of the window
   int m;         // line length
   int n_lines;   // ceil(n / m)

@@ -147,7 +147,7 @@ typedef struct amgb_options {
                                sweeps + residual + restriction (multigrid.hpp:268-282) and
                                ONE for prolongation + add + sweeps (:294-301), each reading
                                the operator from HBM once (register-streaming kernels for
-                               operators that are 3 x 3 stencils over lines, two sweeps);
+                               operators that are 3 x 3 stencils over lines, one or two sweeps);
                                bit 3 (default off): TMA-ring fused legs for the other banded
                                levels; bit 4 (default on): the small coarse levels, the
                                coarsest solve included, run in ONE kernel launch.  The
