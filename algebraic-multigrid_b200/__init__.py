@@ -119,6 +119,7 @@ SIGNATURES = {
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
     "amgb_hierarchy_fused_legs": (_i, [_p, _i]),
     "amgb_hierarchy_tail_first": (_i, [_p]),
+    "amgb_hierarchy_galerkin_device": (_i, [_p, _i, C.POINTER(_d), C.POINTER(_l)]),
     "amgb_hierarchy_leg_plan": (_i, [_p, _i, _i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "amgb_hierarchy_pass_bytes": (_l, [_p, _i]),
     "amgb_hierarchy_vcycle_bytes": (_l, [_p]),
@@ -598,6 +599,12 @@ class Multigrid:
     def fused_legs(self, level):
         """True when `level` runs as one fused kernel per leg (option fuse bit 2)."""
         return bool(lib().amgb_hierarchy_fused_legs(self.h, level))
+
+    def galerkin_device(self, level):
+        """(kernel ms, entries differing from the host-built level + 1) of the device-side R (A P)."""
+        ms, bad = _d(), _l()
+        _check(lib().amgb_hierarchy_galerkin_device(self.h, level, C.byref(ms), C.byref(bad)))
+        return ms.value, bad.value
 
     def tail_first(self):
         """First level of the coarse tail that runs in one launch (-1: none)."""

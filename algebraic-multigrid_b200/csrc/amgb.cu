@@ -18,6 +18,7 @@
 
 #include "host_setup.hpp"
 #include "fused_leg.cuh"
+#include "galerkin_dia.cuh"
 #include "kernels.cuh"
 #include "stream_leg.cuh"
 #include "nccl_dyn.hpp"
@@ -27,6 +28,16 @@ namespace {
 using namespace amgb;
 using amgb::dev::DiaView;
 using amgb::dev::SellView;
+
+// A_H = R (A P) on the DIA layout, one thread per coarse row (galerkin_dia.cuh)
+struct CoarseOffsets {
+  int v[gal::kMaxDiag];
+};
+__global__ void __launch_bounds__(256) k_galerkin_dia(gal::FineDia A, int n_c, int nd_c, CoarseOffsets off_c,
+                                                      double* __restrict__ val_c, int ld_c) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  if (I < n_c) gal::coarse_row(A, n_c, nd_c, off_c.v, I, val_c + I, ld_c);
+}
 
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
@@ -2271,6 +2282,79 @@ int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t*
     info[7] = pl.threads;
     info[8] = (int64_t)pl.smem_bytes;
     info[9] = pl.P.NS;
+  });
+}
+
+// Device-side Galerkin product of one level (not yet part of the
+// setup): computes A_{level+1} = R (A_level P) from the level's device mirror with k_galerkin_dia,
+// times it, and compares every diagonal bit for bit with the mirror of level + 1 that the host
+// setup produced.  mismatches = number of differing entries (0 expected).
+int amgb_hierarchy_galerkin_device(amgb_hierarchy* h, int level, double* ms_out, int64_t* mismatches) {
+  return guarded([&] {
+    if (!h) throw std::invalid_argument("null argument");
+    h->check_level(level, true);
+    h->require_whole(level);
+    h->require_whole(level + 1);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    const DevMat& F = h->ops[level]->rows_of_A();
+    const DevMat& Cm = h->ops[level + 1]->rows_of_A();
+    if (!F.is_dia || !Cm.is_dia || F.dia.rows.p || Cm.dia.rows.p)
+      throw ApiError(AMGB_ESTATE, "the device-side Galerkin product needs the DIA layout");
+    gal::FineDia A;
+    A.n = (int)h->n[level];
+    A.nd = F.dia.n_diag;
+    A.ld = F.dia.ld;
+    for (int d = 0; d < A.nd; ++d) A.off[d] = F.dia.off[d];
+    A.val = F.dia.val.p;
+    CoarseOffsets oc{};
+    const int nd_c = gal::coarse_offsets(A.nd, A.off, oc.v);
+    if (nd_c < 0) throw ApiError(AMGB_ESTATE, "coarse operator has too many diagonals");
+    const int n_c = (int)h->n[level + 1];
+    const int ld_c = (n_c + 31) / 32 * 32;
+    DevBuf<double> out;
+    out.alloc((size_t)nd_c * ld_c);
+    out.zero(h->stream);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    LAUNCH(k_galerkin_dia, blocks_for(n_c, 256), 256, 0, h->stream, A, n_c, nd_c, oc, out.p, ld_c);  // warm-up
+    CUDA_CHECK(cudaEventRecord(e0, h->stream));
+    LAUNCH(k_galerkin_dia, blocks_for(n_c, 256), 256, 0, h->stream, A, n_c, nd_c, oc, out.p, ld_c);
+    CUDA_CHECK(cudaEventRecord(e1, h->stream));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    // compare with the host-built mirror of level + 1, diagonal by diagonal
+    std::vector<double> got((size_t)nd_c * ld_c), want((size_t)Cm.dia.n_diag * Cm.dia.ld);
+    CUDA_CHECK(cudaMemcpy(got.data(), out.p, got.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(want.data(), Cm.dia.val.p, want.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    int64_t bad = 0;
+    std::vector<char> matched(nd_c, 0);
+    for (int d = 0; d < Cm.dia.n_diag; ++d) {
+      int c = -1;
+      for (int k = 0; k < nd_c; ++k)
+        if (oc.v[k] == Cm.dia.off[d]) c = k;
+      if (c < 0) {
+        bad += n_c;
+        continue;
+      }
+      matched[c] = 1;
+      bad += std::memcmp(&got[(size_t)c * ld_c], &want[(size_t)d * Cm.dia.ld], sizeof(double) * n_c) != 0
+                 ? [&] {
+                     int64_t k = 0;
+                     for (int i = 0; i < n_c; ++i)
+                       k += std::memcmp(&got[(size_t)c * ld_c + i], &want[(size_t)d * Cm.dia.ld + i], 8) != 0;
+                     return k;
+                   }()
+                 : 0;
+    }
+    for (int c = 0; c < nd_c; ++c)  // diagonals the host mirror does not have must be all zero
+      if (!matched[c])
+        for (int i = 0; i < n_c; ++i) bad += (got[(size_t)c * ld_c + i] != 0.0);
+    if (mismatches) *mismatches = bad;
   });
 }
 

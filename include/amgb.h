@@ -275,6 +275,12 @@ int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level);
 int amgb_hierarchy_tail_first(const amgb_hierarchy* h);
 int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info);
 
+/* Device-side Galerkin product of one level (measured, not yet used by
+ * the setup): A_{level+1} = R (A_level P) from the level's device mirror, one thread per coarse row,
+ * in the reference's evaluation order (multigrid.hpp:219-223).  Reports the kernel time and the
+ * number of entries that differ bitwise from the host-built mirror of level + 1 (0 expected). */
+int amgb_hierarchy_galerkin_device(amgb_hierarchy* h, int level, double* ms, int64_t* mismatches);
+
 /* counters: kernels launched by this library in this process, and per V-cycle */
 int64_t amgb_kernel_launches(void);
 int64_t amgb_hierarchy_launches_per_vcycle(const amgb_hierarchy* h);

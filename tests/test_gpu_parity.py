@@ -448,6 +448,19 @@ def test_fused_legs_iteration_count_matches_oracle():
     np.testing.assert_allclose(legs.error_history(), mo.history(), rtol=1e-12)
 
 
+@pytest.mark.parametrize("n,L,eps", [(35, 8, 1.0), (100, 9, 1.0), (129, 10, 1e-3), (257, 12, 1.0)])
+def test_device_galerkin_is_bit_identical(n, L, eps):
+    """SURVEY 8f rank 1 building block: A_{l+1} = R (A_l P) computed on the device from the level's
+    DIA mirror equals the host-built (oracle-pinned) coarse operator bit for bit, every level."""
+    mg, _, _ = make_pair(n, L, amg.DampedJacobi(2.0 / 3.0, 2), eps)
+    for l in range(L - 1):
+        if mg.format(l) != "dia" or mg.format(l + 1) != "dia":
+            continue
+        ms, bad = mg.galerkin_device(l)
+        assert bad == 0, (l, bad)
+        assert ms >= 0.0
+
+
 def oracle_pcg(mo, Ao, b, rel_tol, max_iters):
     """CG preconditioned by one oracle V-cycle from a zero guess (test infrastructure)."""
     x = mo.u(0).copy()
