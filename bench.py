@@ -101,8 +101,10 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r[1:] for r in self.rows if t0 is None or t0 <= r[0] <= t1 + 0.05]
         window = "timed region"
-        if not rows:   # region shorter than the sampling period: the samples of the whole run
-            rows, window = [r[1:] for r in self.rows], "whole run (no sample fell into the timed region)"
+        if not rows:   # region shorter than the sampling period: the samples right around it
+            near = [r[1:] for r in self.rows if t0 - 0.25 <= r[0] <= t1 + 0.25] if t0 is not None else []
+            rows = near or [r[1:] for r in self.rows[-3:]]
+            window = "+-0.25 s around the timed region (it is shorter than the sampling period)"
         for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
