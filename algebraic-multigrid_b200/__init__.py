@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libamgb.so")
 OK, EINVAL, ECUDA, ENCCL, ESTATE = 0, 1, 2, 3, 4
 SMOOTHER_GS, SMOOTHER_JACOBI, SMOOTHER_COLOR_GS = 0, 1, 2
 GS_AUTO, GS_LEVELSCHED = 0, 1
+ARITH_REFERENCE, ARITH_FAST = 0, 1
 
 _i, _l, _d, _p = C.c_int, C.c_int64, C.c_double, C.c_void_p
 _pd = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -31,7 +32,7 @@ class Options(C.Structure):
                 ("compute_error_every_n_iters", _l), ("n_iters", _l),
                 ("smoother", _i), ("smoother_iters", _l), ("omega", _d),
                 ("gs_mode", _i), ("use_graph", _i),
-                ("skip_dead_coarse_smooth", _i), ("fuse", _i)]
+                ("skip_dead_coarse_smooth", _i), ("fuse", _i), ("arith", _i)]
 
 
 class AmgbError(RuntimeError):
@@ -60,6 +61,7 @@ SIGNATURES = {
     "amgb_interp_make_operators": (_i, [_l, _l, _pi, _pi, _pd, _pi, _pi, _pd]),
     "amgb_linear_restrict": (_i, [_l, _l, _pd, _pd]),
     "amgb_linear_prolong": (_i, [_l, _l, _pd, _pd]),
+    "amgb_csc_spmv": (_i, [_i, _i, _pi, _pi, _pd, _pd, _pd]),
     "amgb_matrix_create": (_i, [_i, _i, _pi, _pi, _pd, C.POINTER(_p)]),
     "amgb_matrix_destroy": (_i, [_p]),
     "amgb_matrix_nnz_device": (_l, [_p]),
@@ -99,6 +101,10 @@ SIGNATURES = {
     "amgb_hierarchy_get_rhs": (_i, [_p, _i, _p]),
     "amgb_hierarchy_set_soln": (_i, [_p, _i, _p]),
     "amgb_hierarchy_set_rhs": (_i, [_p, _i, _p]),
+    "amgb_hierarchy_get_soln_local": (_i, [_p, _i, _p]),
+    "amgb_hierarchy_get_rhs_local": (_i, [_p, _i, _p]),
+    "amgb_hierarchy_set_soln_local": (_i, [_p, _i, _p]),
+    "amgb_hierarchy_set_rhs_local": (_i, [_p, _i, _p]),
     "amgb_hierarchy_get_coloring": (_i, [_p, _i, C.POINTER(_i), _pi]),
     "amgb_vcycle": (_i, [_p]),
     "amgb_vcycles": (_i, [_p, _l]),
@@ -235,6 +241,26 @@ class LinearInterpolator:
     def get_R(self, level):
         return self._R[level]
 
+    def set_level_to_P(self, level, P):
+        self._P[level] = P
+
+    def set_level_to_R(self, level, R):
+        self._R[level] = R
+
+    # interpolator.hpp:52-68: the STORED operators times the vector (generic device SpMV in
+    # Eigen's order), whatever make_operators put there
+    def prolongation(self, v, level):
+        P = self._P[level]
+        out = np.empty(P.rows)
+        _check(lib().amgb_csc_spmv(P.rows, P.cols, P.colptr, P.rowidx, P.val, _f64(v), out))
+        return out
+
+    def restriction(self, v, level):
+        R = self._R[level]
+        out = np.empty(R.rows)
+        _check(lib().amgb_csc_spmv(R.rows, R.cols, R.colptr, R.rowidx, R.val, _f64(v), out))
+        return out
+
 
 class DeviceMatrix:
     """Device mirror of one CSC matrix (amgb_matrix)."""
@@ -275,14 +301,41 @@ class DeviceMatrix:
         return nc.value, color
 
 
+def _fingerprint(A):
+    """Content fingerprint of a host CSC matrix: every byte of colptr / rowidx / val when the
+    matrix has at most 4 M entries, else 65536 evenly spaced entries of each array (a changed
+    value between the samples is not seen: call invalidate_mirror(A) after editing a large
+    matrix in place)."""
+    import zlib
+    nnz = A.nnz
+    if nnz <= (1 << 22):
+        parts = (A.colptr, A.rowidx, A.val)
+    else:
+        step = max(1, nnz // 65536)
+        parts = (A.colptr[::max(1, A.colptr.shape[0] // 65536)], A.rowidx[::step], A.val[::step])
+    h = 0
+    for a in parts:
+        h = zlib.crc32(np.ascontiguousarray(a).view(np.uint8), h)
+    return (A.rows, A.cols, nnz, h)
+
+
+def invalidate_mirror(A):
+    """Drop the cached device mirror of A (after its values were changed in place)."""
+    A._amgb_mirror = None
+
+
 def _mirror(A):
+    """Device mirror of a host matrix, cached on the object and re-validated against a content
+    fingerprint on every use: values edited in place give a fresh upload, not a stale mirror
+    (the reference always reads the live matrix)."""
     if isinstance(A, DeviceMatrix):
         return A
+    fp = _fingerprint(A)
     cached = getattr(A, "_amgb_mirror", None)
-    if cached is None:
-        cached = DeviceMatrix(A)
-        A._amgb_mirror = cached  # the mirror is cached on the host matrix object
-    return cached
+    if cached is None or cached[0] != fp:
+        cached = (fp, DeviceMatrix(A))
+        A._amgb_mirror = cached
+    return cached[1]
 
 
 def rss(A, u, b):
@@ -395,7 +448,8 @@ class Multigrid:
 
     def __init__(self, interpolator, smoother, A, b, n_levels, tolerance=1e-9,
                  compute_error_every_n_iters=10, n_iters=100, use_graph=True,
-                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18, fuse=None):
+                 skip_dead_coarse_smooth=True, comm=None, min_rows_per_rank=1 << 18, fuse=None,
+                 arith=ARITH_REFERENCE):
         self.interpolator, self.smoother = interpolator, smoother
         o = Options()
         lib().amgb_options_default(C.byref(o))
@@ -411,6 +465,7 @@ class Multigrid:
         o.skip_dead_coarse_smooth = int(skip_dead_coarse_smooth)
         if fuse is not None:
             o.fuse = int(fuse)
+        o.arith = int(arith)
         b = _f64(b)
         h = _p()
         if comm is None:
@@ -467,6 +522,31 @@ class Multigrid:
         f = _f64(f)
         assert f.shape[0] == self.get_n_dofs(level)
         _check(lib().amgb_hierarchy_set_rhs(self.h, level, f.ctypes.data))
+
+    # ---- row-block variants (sharded hierarchies): this rank's rows of local_range only ----
+    def get_soln_local(self, level, out=None):
+        b, e = self.local_range(level)
+        u = np.empty(e - b) if out is None else out
+        _check(lib().amgb_hierarchy_get_soln_local(self.h, level, u.ctypes.data))
+        return u
+
+    def get_rhs_local(self, level, out=None):
+        b, e = self.local_range(level)
+        f = np.empty(e - b) if out is None else out
+        _check(lib().amgb_hierarchy_get_rhs_local(self.h, level, f.ctypes.data))
+        return f
+
+    def set_soln_local(self, level, u):
+        u = _f64(u)
+        b, e = self.local_range(level)
+        assert u.shape[0] == e - b
+        _check(lib().amgb_hierarchy_set_soln_local(self.h, level, u.ctypes.data))
+
+    def set_rhs_local(self, level, f):
+        f = _f64(f)
+        b, e = self.local_range(level)
+        assert f.shape[0] == e - b
+        _check(lib().amgb_hierarchy_set_rhs_local(self.h, level, f.ctypes.data))
 
     def display_error_on(self):
         self.display_error = True

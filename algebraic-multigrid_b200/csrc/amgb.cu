@@ -20,7 +20,7 @@
 #include "fused_leg.cuh"
 #include "galerkin_dia.cuh"
 #include "kernels.cuh"
-#include "stream_leg.cuh"
+#include "stream_leg_api.hpp"
 #include "nccl_dyn.hpp"
 
 namespace {
@@ -586,6 +586,7 @@ void options_default(amgb_options* o) {
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
   o->fuse = 1 | 4 | 16;  // zero-guess sweep, streaming legs, coarse tail; prolongation fusion (bit 1) measured slower
+  o->arith = AMGB_ARITH_REFERENCE;
 }
 
 }  // namespace
@@ -672,7 +673,11 @@ struct amgb_hierarchy {
   unsigned long long* peer_flags_lo = nullptr;  // rank g-1's flags array
   unsigned long long* peer_flags_hi = nullptr;  // rank g+1's flags array
   DevBuf<unsigned long long> epochs;     // [site][2]
-  DevBuf<int> timed_out;
+  // set by a kernel whose wait for a neighbour gave up; pinned host memory mapped into the device,
+  // so the host checks it after every synchronise without a copy
+  int* timed_out_host = nullptr;
+  int* timed_out_dev = nullptr;
+  long long halo_timeout_cycles = 8000000000ll;  // ~4 s of clock64; AMGB_HALO_TIMEOUT_MS overrides
   int n_sites = 0, site_cursor = 0;
   static constexpr int kMaxSites = 4096;
   // second stream: the halo exchange of a sweep runs beside the sweep of the block interior
@@ -690,6 +695,14 @@ struct amgb_hierarchy {
     for (cudaEvent_t e : ev_leg) cudaEventDestroy(e);
     if (aux_stream) cudaStreamDestroy(aux_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (timed_out_host) cudaFreeHost(timed_out_host);
+  }
+  // Call after a stream synchronise: a halo wait that gave up means a neighbour died or stalled
+  // and the vectors hold stale halos -- fail the call instead of returning them.
+  void check_halo() const {
+    if (timed_out_host && *(volatile int*)timed_out_host)
+      throw ApiError(AMGB_ENCCL, "halo exchange timed out waiting for a neighbouring rank "
+                                 "(AMGB_HALO_TIMEOUT_MS); the level vectors are invalid");
   }
   // Map the neighbours' level vectors and flag arrays into this process.
   void setup_p2p() {
@@ -705,15 +718,20 @@ struct amgb_hierarchy {
     for (cudaEvent_t& e : ev_leg) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const char* ov = std::getenv("AMGB_OVERLAP");
     overlap = !(ov && std::string(ov) == "0");
+    if (const char* tmo = std::getenv("AMGB_HALO_TIMEOUT_MS")) {
+      const double ms = std::atof(tmo);
+      if (ms > 0) halo_timeout_cycles = (long long)(ms * 2.0e6);  // clock64 ticks at ~2 GHz
+    }
     const char* env = std::getenv("AMGB_HALO");
     if (env && std::string(env) == "nccl") return;
     const int G = world(), g = rank();
-    flags.alloc((size_t)kMaxSites * 2);
+    flags.alloc((size_t)kMaxSites * 4);  // [site][bumped by lower / upper neighbour][arrived, data]
     flags.zero(stream);
     epochs.alloc((size_t)kMaxSites * 2);
     epochs.zero(stream);
-    timed_out.alloc(1);
-    timed_out.zero(stream);
+    CUDA_CHECK(cudaHostAlloc(&timed_out_host, sizeof(int), cudaHostAllocMapped));
+    *timed_out_host = 0;
+    CUDA_CHECK(cudaHostGetDevicePointer(&timed_out_dev, timed_out_host, 0));
     // handles: per rank [flags, then u, tmp and fw of every sharded level]
     const int per_rank = 1 + 3 * n_sharded;
     const size_t hb = sizeof(cudaIpcMemHandle_t);  // 64 bytes = 8 doubles
@@ -813,17 +831,17 @@ struct amgb_hierarchy {
         lo.peer_dst = peers[l].lo[v] + peers[l].lo_halo_lo + peers[l].lo_n_own;
         lo.src = base + S.halo_lo;
         lo.count = up_cnt;
-        lo.peer_flag = peer_flags_lo + 2 * site + 1;  // "bumped by your upper neighbour"
-        lo.my_flag = flags.p + 2 * site + 0;
+        lo.peer_flag = peer_flags_lo + 4 * site + 2;  // "bumped by your upper neighbour"
+        lo.my_flag = flags.p + 4 * site + 0;
       }
       if (g + 1 < G) {  // my last rows -> rank g+1's lower halo
         hi.peer_dst = peers[l].hi[v];
         hi.src = base + S.halo_lo + S.n_own - dn_cnt;
         hi.count = dn_cnt;
-        hi.peer_flag = peer_flags_hi + 2 * site + 0;  // "bumped by your lower neighbour"
-        hi.my_flag = flags.p + 2 * site + 1;
+        hi.peer_flag = peer_flags_hi + 4 * site + 0;  // "bumped by your lower neighbour"
+        hi.my_flag = flags.p + 4 * site + 2;
       }
-      LAUNCH(dev::k_halo_exchange, 2, 1024, 0, s, lo, hi, epochs.p + 2 * site, timed_out.p);
+      LAUNCH(dev::k_halo_exchange, 2, 1024, 0, s, lo, hi, epochs.p + 2 * site, timed_out_dev, halo_timeout_cycles);
       return;
     }
     NCCL_CHECK(nc.GroupStart());
@@ -1020,59 +1038,13 @@ struct amgb_hierarchy {
     if (pl.P.nd <= 6) go(std::integral_constant<int, 6>());
     else go(std::integral_constant<int, 10>());
   }
-  // ---- register-streaming legs (stream_leg.cuh)
-  // action 0: does a kernel exist for (kind, mask)?  1: launch.  2: set the L1 carve-out (outside
-  // stream capture) and report the resident warps per SM the register count allows.
-  template <int KIND, unsigned MASK>
-  static void sleg_do(const sleg::Params& P, cudaStream_t s, int action, int* warps_per_sm) {
-    if (P.nu == 1) sleg_do_nu<KIND, MASK, 1>(P, s, action, warps_per_sm);
-    else sleg_do_nu<KIND, MASK, 2>(P, s, action, warps_per_sm);
-  }
-  template <int KIND, unsigned MASK, int NU>
-  static void sleg_do_nu(const sleg::Params& P, cudaStream_t s, int action, int* warps_per_sm) {
-    // five-point up leg: three lines in flight at 12 warps/SM measured 6 % faster than two at 16
-    if (NU == 2 && MASK == sleg::kMask5 && env_int("AMGB_SLEG_PF", KIND == sleg::UP ? 3 : 2) == 3) {
-      auto kern3 = sleg::k_stream_leg<KIND, MASK, 2, 3>;
-      if (action == 1) {
-        LAUNCH(kern3, (P.n_warps + 3) / 4, 128, 0, s, P);
-      } else if (action == 2) {
-        cudaFuncAttributes fa{};
-        CUDA_CHECK(cudaFuncGetAttributes(&fa, kern3));
-        if (warps_per_sm) *warps_per_sm = std::max(1, 65536 / (std::max(fa.numRegs, 1) * 128)) * 4;
-        CUDA_CHECK(cudaFuncSetAttribute(kern3, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxL1));
-      }
-      return;
-    }
-    auto kern = sleg::k_stream_leg<KIND, MASK, NU>;
-    if (action == 1) {
-      LAUNCH(kern, (P.n_warps + 3) / 4, 128, 0, s, P);
-    } else if (action == 2) {
-      cudaFuncAttributes fa{};
-      CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
-      if (warps_per_sm) *warps_per_sm = std::max(1, 65536 / (std::max(fa.numRegs, 1) * 128)) * 4;
-      // no shared memory: leave the whole array to the L1 (neighbouring warps' halo columns hit there)
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxL1));
-    }
-  }
-  template <int KIND>
-  static bool sleg_dispatch_mask(unsigned mask, const sleg::Params& P, cudaStream_t s, int action, int* wps) {
-    switch (mask) {
-      case sleg::kMask5: sleg_do<KIND, sleg::kMask5>(P, s, action, wps); return true;
-      case sleg::kMask7a: sleg_do<KIND, sleg::kMask7a>(P, s, action, wps); return true;
-      case sleg::kMask7b: sleg_do<KIND, sleg::kMask7b>(P, s, action, wps); return true;
-      case sleg::kMask9: sleg_do<KIND, sleg::kMask9>(P, s, action, wps); return true;
-      default: return false;
-    }
-  }
-  static bool sleg_dispatch(int kind, unsigned mask, const sleg::Params& P, cudaStream_t s, int action,
-                            int* wps = nullptr) {
-    switch (kind) {
-      case sleg::DOWN_U: return sleg_dispatch_mask<sleg::DOWN_U>(mask, P, s, action, wps);
-      case sleg::DOWN_ZERO: return sleg_dispatch_mask<sleg::DOWN_ZERO>(mask, P, s, action, wps);
-      default: return sleg_dispatch_mask<sleg::UP>(mask, P, s, action, wps);
-    }
+  // ---- register-streaming legs (stream_leg.cuh, compiled in legs.cu)
+  bool fast_arith() const { return opt.arith == AMGB_ARITH_FAST; }
+  bool sleg_dispatch(int kind, unsigned mask, const sleg::Params& P, cudaStream_t s, int action,
+                     int* wps = nullptr) const {
+    const bool done = sleg::dispatch(kind, mask, P, s, action, wps, fast_arith());
+    if (done && action == 1) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return done;
   }
   void leg_down(int l, cudaStream_t s) {
     const LegLevel& G = legs[l];
@@ -1143,6 +1115,7 @@ struct amgb_hierarchy {
         P.omega = opt.omega;
         P.val = W.val.p;
         P.f = S.fw.p;
+        P.finish(W.n_diag);
         return P;
       };
       G.sdown = plan(kind_down, kind_down == leg::DOWN_U ? nu + 1 : nu, 1);
@@ -1197,6 +1170,7 @@ struct amgb_hierarchy {
             P.omega = opt.omega;
             P.val = A.dia.val.p;
             P.f = S.f.p;
+            P.finish(A.dia.n_diag);
             return P;
           };
           G.sdown = plan(kind_down, kind_down == leg::DOWN_U ? nu + 1 : nu, 1);
@@ -1398,16 +1372,12 @@ struct amgb_hierarchy {
     double out = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(&out, scalar.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
+    check_halo();
     return out;
   }
   double rss() {
     LevelState& S = lv[0];
-    if (S.sharded) {
-      const int keep = site_cursor;
-      site_cursor = kMaxSites - 1;  // reserved site for exchanges outside the V-cycle
-      exchange(0, S.u.p, stream);
-      site_cursor = keep;
-    }
+    if (S.sharded) exchange_outside_cycle(0, S.u.p);
     ops[0]->rss(S.u_own(), S.f.p, partial.p, scalar.p, stream);
     return S.sharded ? finish_scalar() : finish_scalar_local();
   }
@@ -1455,21 +1425,62 @@ struct amgb_hierarchy {
     CUDA_CHECK(cudaMemcpyAsync(S.f.p, full + S.s, sizeof(double) * S.n_mat, cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
   }
+  DevBuf<double> gather_buf;  // full-length staging vector of the sharded getters (allocated on first use)
   void download(int l, bool want_u, double* full) {
     LevelState& S = lv[l];
     if (!S.sharded) {
       CUDA_CHECK(cudaMemcpyAsync(full, want_u ? S.u.p : S.f.p, sizeof(double) * n[l],
                                  cudaMemcpyDeviceToHost, stream));
     } else {
-      DevBuf<double> whole;
-      whole.alloc(n[l]);
-      CUDA_CHECK(cudaMemcpyAsync(whole.p + S.s, want_u ? S.u_own() : S.f.p, sizeof(double) * S.n_own,
+      // every rank returns the whole vector: gather the blocks over NVLink into a persistent
+      // staging vector, then one D2H copy.  (Callers that own a row block use download_local.)
+      if (gather_buf.n < (size_t)n[l]) gather_buf.alloc(n[l]);
+      CUDA_CHECK(cudaMemcpyAsync(gather_buf.p + S.s, want_u ? S.u_own() : S.f.p, sizeof(double) * S.n_own,
                                  cudaMemcpyDeviceToDevice, stream));
-      allgather_blocks(whole.p, plan.start[l], stream);
-      CUDA_CHECK(cudaMemcpyAsync(full, whole.p, sizeof(double) * n[l], cudaMemcpyDeviceToHost, stream));
-      CUDA_CHECK(cudaStreamSynchronize(stream));
+      allgather_blocks(gather_buf.p, plan.start[l], stream);
+      CUDA_CHECK(cudaMemcpyAsync(full, gather_buf.p, sizeof(double) * n[l], cudaMemcpyDeviceToHost, stream));
     }
     CUDA_CHECK(cudaStreamSynchronize(stream));
+    check_halo();
+  }
+  // this rank's rows [s, e) only: no collective, 1/world of the bytes
+  void download_local(int l, bool want_u, double* block) {
+    LevelState& S = lv[l];
+    CUDA_CHECK(cudaMemcpyAsync(block, want_u ? S.u_own() : S.f.p, sizeof(double) * S.n_own,
+                               cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    check_halo();
+  }
+  // out-of-cycle halo exchange of a level vector (reserved site; collective over the ranks)
+  void exchange_outside_cycle(int l, double* base) {
+    const int keep = site_cursor;
+    site_cursor = kMaxSites - 1;
+    exchange(l, base, stream);
+    site_cursor = keep;
+  }
+  void upload_local(int l, bool want_u, const double* block) {
+    LevelState& S = lv[l];
+    if (want_u) {
+      CUDA_CHECK(cudaMemcpyAsync(S.u_own(), block, sizeof(double) * S.n_own, cudaMemcpyHostToDevice, stream));
+      if (S.sharded) exchange_outside_cycle(l, S.u.p);
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(S.f.p, block, sizeof(double) * S.n_own, cudaMemcpyHostToDevice, stream));
+      if (S.sharded) {
+        if (S.fw.p) {
+          CUDA_CHECK(cudaMemcpyAsync(S.fw.p + S.halo_lo, S.f.p, sizeof(double) * S.n_own, cudaMemcpyDeviceToDevice,
+                                     stream));
+          exchange_outside_cycle(l, S.fw.p);
+          // the per-operator kernels read f on the ghost rows [n_own, n_mat) too
+          if (S.n_mat > S.n_own)
+            CUDA_CHECK(cudaMemcpyAsync(S.f.p + S.n_own, S.fw.p + S.halo_lo + S.n_own,
+                                       sizeof(double) * (S.n_mat - S.n_own), cudaMemcpyDeviceToDevice, stream));
+        } else if (S.n_mat > S.n_own) {
+          throw ApiError(AMGB_ESTATE, "set_rhs_local needs the window layout on this level");
+        }
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    check_halo();
   }
 };
 
@@ -1555,6 +1566,31 @@ int amgb_linear_prolong(int64_t n_h, int64_t n_H, const double* e, double* out) 
     if (n_h)
       LAUNCH(dev::k_prolong_add, blocks_for(n_h, 256), 256, 0, nullptr, de.p, 0, (int)n_H, dout.p, 0, (int)n_h);
     dout.download(out, nullptr);
+    CUDA_CHECK(cudaStreamSynchronize(nullptr));
+  });
+}
+
+// y = A x for any CSC matrix (rectangular too), Eigen's evaluation order: the stored P / R of an
+// InterpolatorBase applied as get_P(level) * v (interpolator.hpp:52-68).  One-shot: the matrix
+// is mirrored (rows of A, SELL-32 or DIA), applied and dropped.
+int amgb_csc_spmv(int n_rows, int n_cols, const int* colptr, const int* rowidx, const double* val,
+                  const double* x, double* y) {
+  return guarded([&] {
+    if (!colptr || !x || !y || n_rows < 0 || n_cols < 0) throw std::invalid_argument("bad spmv arguments");
+    require_device();
+    Csc AT = transpose(csc_from_arrays(n_rows, n_cols, colptr, rowidx, val));  // column k of AT = row k of A
+    DevMat M;
+    M.upload(AT, nullptr, nullptr);
+    DevBuf<double> dx, dy;
+    dx.upload(x, n_cols, nullptr);
+    dy.alloc(n_rows);
+    if (n_rows)
+      with_view(M, [&](auto V) {
+        auto kern = dev::k_spmv<decltype(V)>;
+        V.n_rows = n_rows;
+        LAUNCH(kern, blocks_for(n_rows, 256), 256, 0, nullptr, V, dx.p, dy.p);
+      });
+    dy.download(y, nullptr);
     CUDA_CHECK(cudaStreamSynchronize(nullptr));
   });
 }
@@ -1888,10 +1924,9 @@ int amgb_hierarchy_halo_mode(const amgb_hierarchy* h) {
   return h->p2p ? AMGB_HALO_PEER : AMGB_HALO_NCCL;
 }
 int amgb_hierarchy_halo_timed_out(amgb_hierarchy* h) {
-  if (!h || !h->p2p) return 0;
-  int v = 0;
-  cudaMemcpy(&v, h->timed_out.p, sizeof(int), cudaMemcpyDeviceToHost);
-  return v;
+  if (!h || !h->timed_out_host) return 0;
+  cudaStreamSynchronize(h->stream);
+  return *(volatile int*)h->timed_out_host;
 }
 
 // ---- communicator ----
@@ -2023,6 +2058,40 @@ int amgb_hierarchy_set_rhs(amgb_hierarchy* h, int level, const double* f) {
     h->upload_f(level, f);
   });
 }
+// this rank's row block [begin, end) of amgb_hierarchy_local_range only (whole vector when the
+// level is not sharded): no collective, 1/world of the host<->device bytes
+int amgb_hierarchy_get_soln_local(amgb_hierarchy* h, int level, double* u_block) {
+  return guarded([&] {
+    if (!h || !u_block) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->download_local(level, true, u_block);
+  });
+}
+int amgb_hierarchy_get_rhs_local(amgb_hierarchy* h, int level, double* f_block) {
+  return guarded([&] {
+    if (!h || !f_block) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->download_local(level, false, f_block);
+  });
+}
+int amgb_hierarchy_set_soln_local(amgb_hierarchy* h, int level, const double* u_block) {
+  return guarded([&] {
+    if (!h || !u_block) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->upload_local(level, true, u_block);
+  });
+}
+int amgb_hierarchy_set_rhs_local(amgb_hierarchy* h, int level, const double* f_block) {
+  return guarded([&] {
+    if (!h || !f_block) throw std::invalid_argument("null argument");
+    h->check_level(level);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->upload_local(level, false, f_block);
+  });
+}
 int amgb_hierarchy_get_coloring(const amgb_hierarchy* h, int level, int* n_colors, int* color) {
   return guarded([&] {
     if (!h) throw std::invalid_argument("null argument");
@@ -2047,6 +2116,7 @@ int amgb_vcycles(amgb_hierarchy* h, int64_t count) {
     CUDA_CHECK(cudaSetDevice(h->device));
     for (int64_t i = 0; i < count; ++i) h->vcycle();
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->check_halo();
   });
 }
 int amgb_hierarchy_rss(amgb_hierarchy* h, double* out) {
@@ -2074,6 +2144,7 @@ int amgb_solve(amgb_hierarchy* h, int64_t* iters_done, double* last_error) {
       }
     }
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->check_halo();
     h->iters_done = iter;
     if (iters_done) *iters_done = iter;
     if (last_error) *last_error = error;
@@ -2097,6 +2168,7 @@ int amgb_solve_relative(amgb_hierarchy* h, double rel_tol, int64_t* iters_done, 
       }
     }
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->check_halo();
     h->iters_done = iter;
     if (iters_done) *iters_done = iter;
     if (last_rel) *last_rel = rel;
@@ -2174,6 +2246,7 @@ int amgb_synchronize(amgb_hierarchy* h) {
   return guarded([&] {
     if (!h) throw std::invalid_argument("null argument");
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->check_halo();
   });
 }
 

@@ -181,6 +181,19 @@ __global__ void __launch_bounds__(256) k_residual(M A, const double* __restrict_
   r[t] = row_residual(A, t, t, u, f[t]);
 }
 
+// ------------------------------------------------------------------ y = A x (generic operator)
+// Eigen's ColMajor sparse x dense product as used by InterpolatorBase::restriction /
+// prolongation (interpolator.hpp:52-68): y zero-initialised, every row accumulates its
+// products in ascending column order from +0.  The view holds the ROWS of the operator.
+template <class M>
+__global__ void __launch_bounds__(256) k_spmv(M A, const double* __restrict__ x, double* __restrict__ y) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.n_rows) return;
+  double acc = 0.0;
+  for_each_entry(A, t, t, x, [&](int, double a, double xv) { acc = __dadd_rn(acc, __dmul_rn(a, xv)); });
+  y[t] = acc;
+}
+
 // ------------------------------------------------------------------ damped Jacobi
 // u_new[k] = u[k] + omega * (r_k / a_kk), r_k as in k_residual.
 // Rows row0 .. (skipping [hole_begin, hole_begin + hole_len)) up to A.n_rows: the sharded
@@ -585,43 +598,66 @@ __global__ void __launch_bounds__(256) k_prolong_add(const double* __restrict__ 
 }
 
 // ------------------------------------------------------------------ peer-memory halo exchange
-// One launch per exchange site.  Block 0 serves the lower neighbour (rank g-1), block 1 the
-// upper one: copy this rank's boundary rows straight into the neighbour's halo region
-// (peer-mapped pointer, stores travel over NVLink), make them visible system-wide, bump the
-// neighbour's epoch flag for this site, then wait until the neighbour has done the same for
-// us.  Epochs live in device memory so a replayed CUDA graph keeps counting.  A rank can be
-// at most one site ahead of its neighbours, and consecutive sites of one level alternate
-// between the two ping-pong vectors, so a halo is never overwritten while it is still read.
+// One launch per exchange site (the stand-alone exchange of the per-operator sharded path and of
+// the out-of-cycle sites; the fused legs push their boundary rows themselves, stream_leg.cuh).
+// Block 0 serves the lower neighbour (rank g-1), block 1 the upper one, in two phases:
+//   1. ARRIVE: bump the neighbour's "arrived" flag for this site and wait for its bump of ours.
+//      A rank arrives only after every earlier kernel of its stream has finished, so from here
+//      on nobody still reads the halo rows this exchange overwrites (no write-after-read hazard
+//      whatever vector the previous site used, e.g. odd sweep counts);
+//   2. DATA: copy this rank's boundary rows straight into the neighbour's halo region
+//      (peer-mapped pointer, stores travel over NVLink), release them system-wide, bump the
+//      neighbour's "data" flag and wait for ours.
+// Epochs live in device memory so a replayed CUDA graph keeps counting.  A wait that exceeds
+// timeout_cycles sets *timed_out; the host turns that into an error (results are invalid).
 struct HaloSide {
   double* peer_dst;               // where my rows go in the neighbour's vector (nullptr: no neighbour)
   const double* src;              // my boundary rows
   int count;                      // doubles to send
-  unsigned long long* peer_flag;  // neighbour's flag for (site, the side I am on from its view)
-  unsigned long long* my_flag;    // my flag the neighbour bumps
+  unsigned long long* peer_flag;  // neighbour's flag pair for (site, the side I am on from its view)
+  unsigned long long* my_flag;    // my flag pair the neighbour bumps: [0] arrived, [1] data
 };
+__device__ __forceinline__ void flag_release(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long flag_acquire(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p >= want; false (and *timed_out = 1) after timeout_cycles
+__device__ __forceinline__ bool flag_wait(const unsigned long long* p, unsigned long long want,
+                                          long long timeout_cycles, int* timed_out) {
+  const long long t0 = clock64();
+  while (flag_acquire(p) < want) {
+    if (clock64() - t0 > timeout_cycles) {  // a neighbour died or stalled: do not hang the GPU
+      *timed_out = 1;
+      return false;
+    }
+    __nanosleep(20);
+  }
+  return true;
+}
 __global__ void __launch_bounds__(1024) k_halo_exchange(HaloSide lo, HaloSide hi, unsigned long long* epoch,
-                                                       int* timed_out) {
+                                                       int* timed_out, long long timeout_cycles) {
   const HaloSide S = blockIdx.x == 0 ? lo : hi;
   if (S.peer_dst == nullptr) return;
+  __shared__ unsigned long long e_sh;
+  if (threadIdx.x == 0) {
+    const unsigned long long e = epoch[blockIdx.x] + 1;
+    epoch[blockIdx.x] = e;
+    e_sh = e;
+    flag_release(S.peer_flag + 0, e);                       // I have arrived at this site
+    flag_wait(S.my_flag + 0, e, timeout_cycles, timed_out);  // so has the neighbour
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < S.count; i += blockDim.x) S.peer_dst[i] = S.src[i];
   // bar.sync orders every thread's peer stores before thread 0's release store below
   // (release is cumulative over what happens-before it), so one system-scope release suffices
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned long long e = epoch[blockIdx.x] + 1;
-    epoch[blockIdx.x] = e;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(S.peer_flag), "l"(e) : "memory");
-    const long long t0 = clock64();
-    unsigned long long seen = 0;
-    while (true) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(S.my_flag) : "memory");
-      if (seen >= e) break;
-      if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour died; do not hang the GPU
-        *timed_out = 1;
-        break;
-      }
-      __nanosleep(20);
-    }
+    flag_release(S.peer_flag + 1, e_sh);
+    flag_wait(S.my_flag + 1, e_sh, timeout_cycles, timed_out);
   }
   __syncthreads();
 }

@@ -1,89 +1,67 @@
 // Register-streaming fused V-cycle legs for the damped-Jacobi cycle (sm_100a).
 //
-// Same job as fused_leg.cuh -- one kernel per level and leg,
+// One kernel per level and leg,
 //   down leg: pre-smoothing sweeps -> residual -> restriction   (multigrid.hpp:268-282)
 //   up leg:   coarse-grid correction -> post-smoothing sweeps    (multigrid.hpp:294-301)
-// with the operator, f and the input vector read from HBM once -- but for the operators whose
-// rows are a 3 x 3 stencil in (line, element) space: every diagonal offset is a*m + delta with
+// with the operator, f and the input vector read from HBM once, for the operators whose rows
+// are a 3 x 3 stencil in (line, element) space: every diagonal offset is a*m + delta with
 // a, delta in {-1,0,1} for a line length m (level 0 of an n x n grid: m = n, five points;
 // level 1: seven points; Galerkin levels >= 2: nine points).
 //
-// A WARP is the unit of work: its 32 lanes are 32 consecutive elements of a line and it
-// streams down a chunk of lines.  The chained stencil stages run one line behind the other in
-// program order (stage s on line jj - s + 1 at step jj); every lane keeps the last three
-// lines of each stage's result for its own element in registers, and the delta = -1 / +1
-// neighbours come from the adjacent lanes by warp shuffles -- no shared memory, no block
-// barriers.  Each stage shrinks the correct lanes by one on both sides, so a warp owns the
-// 32 - 2H middle lanes (H = stages [+ 1 for the restriction]) and neighbouring warps overlap.
-// The operator rows, f and the input of the line PF steps ahead are loaded straight into a
-// register ring (coalesced 256-byte requests per warp and array); the ring is indexed with
-// compile-time slots by unrolling the line loop over its period.  The kernels use no shared
-// memory and ask for the largest L1 carve-out: the halo columns neighbouring warps share are
-// served from L1.  (A variant that prefetched deeper through a per-warp cp.async FIFO in shared
-// memory measured slower at every level -- more load/store-unit work per row and a smaller L1;
-// profiles/r1_stream_legs.md.)
+// A WARP is the unit of work: its 32 lanes are 32 consecutive rows of a line and it streams
+// down a chunk of lines.  The chained stencil stages run one line behind the other in program
+// order (stage s on line jj - s + 1 at step jj); every lane keeps the last three lines of each
+// stage's result for its own element in registers, and the delta = -1 / +1 neighbours come from
+// the adjacent lanes by warp shuffles -- no shared memory, no block barriers.  Each stage
+// shrinks the correct lanes by one on both sides, so a warp owns the 32 - 2H middle lanes
+// (H = stages [+ 1 for the restriction]) and neighbouring warps overlap.  The operator rows, f
+// and the input of the line PF steps ahead are loaded straight into a register ring (coalesced
+// 256-byte requests per warp and array: one IMAD.WIDE + one LDG each, row index clamped to the
+// rows that exist instead of predicating the loads); the ring is indexed with compile-time
+// slots by unrolling the line loop over its period.  The kernels use no shared memory and ask
+// for the largest L1 carve-out: the halo columns neighbouring warps share are served from L1.
 //
-// Per-row arithmetic (operation order, no FMA contraction) is that of k_jacobi /
-// k_jacobi_zero / k_residual_restrict / k_prolong_add (kernels.cuh): bit-identical results.
+// Arithmetic (template flag FAST):
+//   reference order (FAST = false): the per-row operation order of k_jacobi / k_jacobi_zero /
+//     k_residual_restrict / k_prolong_add (kernels.cuh) -- separate multiply and subtract, IEEE
+//     division -- i.e. the CPU oracle's: bit-identical results;
+//   fast (FAST = true, amgb_options.arith = AMGB_ARITH_FAST): fused multiply-adds and
+//     u + (omega / d) r with 1 / d from MUFU.RCP64H plus two Newton steps (full double accuracy up
+//     to ~1 ulp).  Differences to the oracle are rounding-level (~1e-16 per operation); the
+//     contract of the path is 1e-12 relative on the per-level iterates, tests/test_gpu_parity.py.
+//
+// Rows that do not exist (outside the level, or outside the window of a sharded level) are not
+// predicated away: their loads are clamped to the nearest existing row, so they compute finite
+// garbage.  No existing row reads them with a non-zero coefficient (the operator has no entry
+// there), and 0 * finite = 0, so the results of the rows that are stored are unaffected.
+//
+// Multi-GPU (Params::sync.enabled): the edge warps wait for the neighbour's previous site before
+// touching ghost rows and push their boundary rows into the neighbour's ghost rows at the end
+// (stream_leg_api.hpp, struct Sync) -- the halo exchange costs no launch.
 #pragma once
 #include <cstdint>
 
 #include <cuda_runtime.h>
 
+#include "stream_leg_api.hpp"
+
 namespace amgb {
 namespace sleg {
 
-enum Kind { DOWN_U = 0, DOWN_ZERO = 1, UP = 2 };
-
-// stencil slot sl = (a + 1) * 3 + (delta + 1), ascending in column order
-constexpr unsigned kMask5 = 0x0BAu;   // (-1,0) (0,-1) (0,0) (0,1) (1,0): level 0 of an n x n grid, m = n
-constexpr unsigned kMask7a = 0x1BBu;  // level 1 with m = its smaller far offset: (-1,-1) (-1,0) (0,*) (1,0) (1,1)
-constexpr unsigned kMask7b = 0x0FEu;  // level 1 with m = its larger far offset:  (-1,0) (-1,1) (0,*) (1,-1) (1,0)
-constexpr unsigned kMask9 = 0x1FFu;   // Galerkin levels >= 2
-
-struct Params {
-  // The kernel works on a WINDOW of the level: local row k is global row base + k.  A whole level
-  // is the window [0, n) with base 0; a rank of the row-block sharded cycle passes its block plus
-  // the ghost rows on both sides (whose inputs a halo exchange has filled) and stores results for
-  // its own rows only -- the ghost rows are recomputed redundantly, like the lanes at a warp's edge.
-  int base;       // global row of local row 0 (may be negative: rows before the level start)
-  int n_global;   // rows of the level
-  int own_begin;  // local rows [own_begin, own_end) are stored
-  int own_end;
-  int cbase;      // global coarse index of fc[0] and e[0]
-  int n_e;        // entries of e / fc that exist locally
-  int nu;         // Jacobi sweeps per smooth call (selects the kernel instantiation on the host)
-  int n;         // rows of the window
-  int m;         // line length
-  int n_lines;   // ceil(n / m)
-  int Wu;        // owned elements per warp (32 - 2H)
-  int n_strips;  // ceil(m / Wu)
-  int LJ;        // lines per chunk
-  int n_chunks;
-  int n_warps;   // n_strips * n_chunks
-  int ld;
-  int n_coarse;
-  double omega;
-  const double* val;
-  const double* f;
-  const double* uin;
-  const double* e;
-  double* uout;
-  double* fc;
-};
-
-__host__ __device__ constexpr int popc9(unsigned v) {
-  int c = 0;
-  for (int i = 0; i < 9; ++i) c += (v >> i) & 1u;
-  return c;
+__device__ __forceinline__ double rcp_refined(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));  // MUFU.RCP64H: ~20 good bits
+  double e = __fma_rn(-d, r, 1.0);
+  r = __fma_rn(r, e, r);
+  e = __fma_rn(-d, r, 1.0);
+  return __fma_rn(r, e, r);
 }
 
-template <int KIND, unsigned MASK, int NU, int PF_ = 2>
+template <int KIND, unsigned MASK, int NU, int PF_, bool FAST>
 struct Leg {
   static constexpr int ND = popc9(MASK);
-  static constexpr int NS = (KIND == DOWN_U) ? NU + 1 : NU;  // chained stencil stages
-  static constexpr int X = (KIND == UP) ? 0 : 1;
-  static constexpr int H = NS + X;                           // lanes lost on each side
+  static constexpr int NS = stages(KIND, NU);                // chained stencil stages
+  static constexpr int H = lost_lanes(KIND, NU);             // lanes lost on each side
   static constexpr int PF = PF_;                             // lines in flight
   static constexpr int RS = NS + 1 + PF;                     // register-ring slots
   static constexpr int DC = popc9(MASK & 0xFu);              // rank of the centre slot (0,0)
@@ -95,40 +73,67 @@ struct Leg {
     double f, u, e0, e1;
   };
 
-  static __device__ __forceinline__ void load(Line& L, const Params& P, int g, int lane) {
-    const int k = g + lane;
-    const int kg = k + P.base;
-    const bool ok = (k >= 0 && k < P.n && kg >= 0 && kg < P.n_global);
-    const double* vp = P.val + k;
+  // ---- arithmetic ----
+  static __device__ __forceinline__ double mulsub(double acc, double a, double x) {
+    if constexpr (FAST) return __fma_rn(-a, x, acc);
+    else return __dsub_rn(acc, __dmul_rn(a, x));
+  }
+  // x + omega * (r / d); rows without a diagonal keep x (smoother semantics of kernels.cuh)
+  static __device__ __forceinline__ double relax(double x, double r, double d, double omega) {
+    if constexpr (FAST) {
+      const double w = omega * rcp_refined(d);
+      return (d == 0.0) ? x : __fma_rn(w, r, x);
+    } else {
+      return (d == 0.0) ? x : __dadd_rn(x, __dmul_rn(omega, __ddiv_rn(r, d)));
+    }
+  }
+  // first sweep from the zero guess: omega * (f / d)
+  static __device__ __forceinline__ double relax_zero(double f, double d, double omega) {
+    if constexpr (FAST) return (d == 0.0) ? 0.0 : f * (omega * rcp_refined(d));
+    else return (d == 0.0) ? 0.0 : __dmul_rn(omega, __ddiv_rn(f, d));
+  }
+
+  static __device__ __forceinline__ bool e_exists(const Params& P, int Jl) {
+    return (unsigned)(Jl - P.e_lo) < (unsigned)P.e_cnt;
+  }
+
+  // loads of the line whose row on this lane is k (clamped to the rows that exist)
+  static __device__ __forceinline__ void load(Line& L, const Params& P, int k) {
+    const int kc = min(max(k, P.row_lo), P.row_hi1);
 #pragma unroll
-    for (int d = 0; d < ND; ++d) L.a[d] = ok ? __ldg(vp + (size_t)d * P.ld) : 0.0;
-    L.f = ok ? __ldg(P.f + k) : 0.0;
-    if (KIND != DOWN_ZERO) L.u = ok ? __ldg(P.uin + k) : 0.0;
+    for (int d = 0; d < ND; ++d) L.a[d] = __ldg(P.vd[d] + kc);
+    L.f = __ldg(P.f + kc);
+    if (KIND != DOWN_ZERO) L.u = __ldg(P.uin + kc);
     if (KIND == UP) {
       // (P e)[k]: odd k: 1 e[J]; even k: .5 e[J-1] + .5 e[J], J = k >> 1, terms outside
       // [0, n_coarse) absent (interpolator.hpp:118-125)
-      const int J = kg >> 1, Jl = J - P.cbase;
-      L.e0 = (ok && !(kg & 1) && J - 1 >= 0 && J - 1 < P.n_coarse && Jl - 1 >= 0 && Jl - 1 < P.n_e)
-                 ? __ldg(P.e + Jl - 1) : 0.0;
-      L.e1 = (ok && J < P.n_coarse && Jl >= 0 && Jl < P.n_e) ? __ldg(P.e + Jl) : 0.0;
+      const int Jl = ((kc + P.base) >> 1) - P.cbase;
+      const int last = P.e_lo + (P.e_cnt > 0 ? P.e_cnt - 1 : 0);
+      L.e1 = __ldg(P.e + min(max(Jl, P.e_lo), last));
+      L.e0 = __ldg(P.e + min(max(Jl - 1, P.e_lo), last));
     }
   }
 
-  // input value of a row (stage 0)
-  static __device__ __forceinline__ double input(const Line& L, const Params& P, int k) {
+  // input value of a row (stage 0); kg = global row
+  static __device__ __forceinline__ double input(const Line& L, const Params& P, int kg) {
     if (KIND == DOWN_U) return L.u;
-    if (KIND == DOWN_ZERO) {
-      const double d = L.a[DC];
-      return (d == 0.0) ? 0.0 : __dmul_rn(P.omega, __ddiv_rn(L.f, d));
-    }
-    double acc = 0.0;
-    if (k & 1) {
-      acc = __dadd_rn(acc, __dmul_rn(1.0, L.e1));
+    if (KIND == DOWN_ZERO) return relax_zero(L.f, L.a[DC], P.omega);
+    const int Jl = (kg >> 1) - P.cbase;
+    const bool odd = kg & 1;
+    const double e1 = e_exists(P, Jl) ? L.e1 : 0.0;
+    const double e0 = (!odd && e_exists(P, Jl - 1)) ? L.e0 : 0.0;
+    if constexpr (FAST) {
+      return odd ? L.u + e1 : __fma_rn(0.5, e0 + e1, L.u);
     } else {
-      acc = __dadd_rn(acc, __dmul_rn(0.5, L.e0));
-      acc = __dadd_rn(acc, __dmul_rn(0.5, L.e1));
+      double acc = 0.0;
+      if (odd) {
+        acc = __dadd_rn(acc, __dmul_rn(1.0, e1));
+      } else {
+        acc = __dadd_rn(acc, __dmul_rn(0.5, e0));
+        acc = __dadd_rn(acc, __dmul_rn(0.5, e1));
+      }
+      return __dadd_rn(L.u, acc);
     }
-    return __dadd_rn(L.u, acc);
   }
 
   template <int SL>
@@ -140,9 +145,8 @@ struct Leg {
       double xv = xl;
       if constexpr (dl < 0) xv = __shfl_up_sync(0xffffffffu, xl, 1);
       if constexpr (dl > 0) xv = __shfl_down_sync(0xffffffffu, xl, 1);
-      // an absent entry is stored as 0.0 and every x a valid row can see is finite (invalid rows
-      // carry zeros), so acc - 0 * x == acc bit for bit: no test, no select
-      acc = __dsub_rn(acc, __dmul_rn(L.a[d], xv));
+      // an absent entry is stored as 0.0 and every x is finite, so acc - 0 * x == acc: no test, no select
+      acc = mulsub(acc, L.a[d], xv);
     }
   }
   // f - sum a x over the row, ascending column order
@@ -181,91 +185,170 @@ struct Leg {
     }
   }
 
+  // what a warp stores: local rows [st_lo, st_lo + st_cnt) on its owned lanes
+  struct Own {
+    int st_lo;
+    unsigned st_cnt;
+    bool lane;
+    __device__ __forceinline__ bool operator()(int k) const { return lane && (unsigned)(k - st_lo) < st_cnt; }
+  };
+
   // One step: loads of line jj + 1 + PF, input stage on line jj + 1 (ring slot P_), stage s on
-  // line jj - s + 1 (slot P_ - s), restriction of the residual line.  g1 = first row of line jj + 1.
+  // line jj - s + 1 (slot P_ - s), restriction of the residual line.  k1 = this lane's row on line jj + 1.
   template <int P_>
-  static __device__ __forceinline__ void step(State& S, const Params& P, int jj, int g1, int lane, int j0, int j1,
-                                              int own_lo, int own_hi) {
+  static __device__ __forceinline__ void step(State& S, const Params& P, int k1, const Own& own) {
     const int m = P.m;
-    load(S.R[(P_ + PF) % RS], P, g1 + PF * m, lane);
-    const bool own_lane = (lane >= own_lo && lane < own_hi);
+    load(S.R[(P_ + PF) % RS], P, k1 + PF * m);
     // ---- input stage, line jj + 1
     {
       const Line& L = S.R[P_ % RS];
-      const int k = g1 + lane;
-      const double in = input(L, P, k + P.base);
+      const double in = input(L, P, k1 + P.base);
       push(S.w[0], in, P_);
-      if (S_OUT == 0 && own_lane && jj + 1 >= j0 && jj + 1 < j1 && k >= P.own_begin && k < P.own_end) P.uout[k] = in;
+      if (S_OUT == 0 && own(k1)) P.uout[k1] = in;
     }
 #pragma unroll
     for (int s = 1; s <= NS; ++s) {
       const Line& L = S.R[(P_ - s + 2 * RS) % RS];
-      const int j = jj - s + 1;
-      const int k = g1 - s * m + lane;
+      const int k = k1 - s * m;
       const double acc = stencil(L, S.w[s - 1][WM(P_)], S.w[s - 1][W0(P_)], S.w[s - 1][WP(P_)]);
-      const bool own = own_lane && j >= j0 && j < j1 && k >= P.own_begin && k < P.own_end;
       if (KIND != UP && s == NS) {
         // residual -> restriction: f_c[J] = (.5 r[2J] + r[2J+1]) + .5 r[2J+2]   (interpolator.hpp:64-68)
         const double rm = __shfl_up_sync(0xffffffffu, acc, 1);
         const double rp = __shfl_down_sync(0xffffffffu, acc, 1);
         const int kg = k + P.base;
-        if (own && (kg & 1)) {
+        if (own(k) && (kg & 1)) {
           const int J = (kg - 1) >> 1;
-          if (J < P.n_coarse) P.fc[J - P.cbase] = __dadd_rn(__dadd_rn(__dmul_rn(0.5, rm), acc), __dmul_rn(0.5, rp));
+          if (J < P.n_coarse) {
+            if constexpr (FAST) P.fc[J - P.cbase] = __fma_rn(0.5, rm + rp, acc);
+            else P.fc[J - P.cbase] = __dadd_rn(__dadd_rn(__dmul_rn(0.5, rm), acc), __dmul_rn(0.5, rp));
+          }
         }
       } else {
-        const double diag = L.a[DC];
-        const double xc = S.w[s - 1][W0(P_)];
-        const double out = (diag == 0.0) ? xc : __dadd_rn(xc, __dmul_rn(P.omega, __ddiv_rn(acc, diag)));
+        const double out = relax(S.w[s - 1][W0(P_)], acc, L.a[DC], P.omega);
         if (s < NS) push(S.w[s], out, P_);
-        if (s == S_OUT && own) P.uout[k] = out;
+        if (s == S_OUT && own(k)) P.uout[k] = out;
       }
     }
   }
 
   // RS consecutive steps (one period of the register ring); `left` counts the steps still to
-  // do and is the same for every warp of the grid, so control flow stays convergent and the
+  // do and is the same for every lane of the warp, so control flow stays convergent and the
   // shuffles need no re-convergence code.
   template <int P_>
-  static __device__ __forceinline__ void steps(State& S, const Params& P, int& jj, int& g1, int& left, int lane, int j0,
-                                               int j1, int own_lo, int own_hi) {
+  static __device__ __forceinline__ void steps(State& S, const Params& P, int& k1, int& left, const Own& own) {
     if constexpr (P_ < RS) {
       if (left <= 0) return;
-      step<P_>(S, P, jj, g1, lane, j0, j1, own_lo, own_hi);
-      ++jj;
+      step<P_>(S, P, k1, own);
       --left;
-      g1 += P.m;
-      steps<P_ + 1>(S, P, jj, g1, left, lane, j0, j1, own_lo, own_hi);
+      k1 += P.m;
+      steps<P_ + 1>(S, P, k1, left, own);
+    }
+  }
+
+  // ---- multi-GPU: waits and pushes of the edge warps (struct Sync)
+  // Branch-free on the warp's role and convergent for the compiler (the loop exits on warp
+  // votes), so the shuffles of the line loop that follows need no re-convergence code: a warp
+  // that is not at this edge polls its own epoch word, which equals the value waited for.
+  static __device__ __forceinline__ void wait_side(const Sync& Y, int side, bool edge) {
+    const unsigned long long* epoch_word = Y.wait_epoch[side];
+    const unsigned long long* flag = (edge && Y.wait_flag[side] != nullptr) ? Y.wait_flag[side] : epoch_word;
+    const unsigned long long want = *epoch_word;
+    const long long t0 = clock64();
+    while (true) {
+      unsigned long long seen;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      if (__all_sync(0xffffffffu, seen >= want)) break;
+      if (__any_sync(0xffffffffu, clock64() - t0 > Y.timeout_cycles)) {  // a neighbour died or stalled
+        *Y.timed_out = 1;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  static __device__ __forceinline__ void signal_side(const Sync& Y, int side, int lane) {
+    // every lane's peer stores are fenced system-wide before lane 0 counts the warp as done
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned prev = atomicAdd(Y.done[side], 1u);
+      if (prev + 1u == (unsigned)Y.expected[side]) {
+        *Y.done[side] = 0u;      // the next launch of this site starts from zero (stream order)
+        __threadfence_system();  // cumulativity: the other edge warps' stores are ordered before the flag
+        const unsigned long long e = *Y.epoch[side] + 1ull;
+        *Y.epoch[side] = e;
+        if (Y.peer_flag[side] != nullptr)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(Y.peer_flag[side]), "l"(e) : "memory");
+      }
+    }
+  }
+  // push the rows / coarse entries this warp stored that a neighbour keeps as ghosts: each lane
+  // re-reads what it wrote itself (L1/L2 hits) -- the hot loop carries no push code
+  static __device__ __forceinline__ void push_rows(const Params& P, int k_first, int j0, int j1, const Own& own) {
+    const Sync& Y = P.sync;
+    for (int j = j0, k = k_first; j < j1; ++j, k += P.m) {
+      if (!own(k)) continue;
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const Push& U = Y.push_u[side];
+        if (U.dst != nullptr && k >= U.begin && k < U.end) U.dst[k] = P.uout[k];
+        if (KIND != UP) {
+          const Push& F = Y.push_fc[side];
+          const int kg = k + P.base;
+          if (F.dst != nullptr && (kg & 1)) {
+            const int Jl = ((kg - 1) >> 1) - P.cbase;
+            if (Jl >= F.begin && Jl < F.end && Jl + P.cbase < P.n_coarse) F.dst[Jl] = P.fc[Jl];
+          }
+        }
+      }
     }
   }
 
   static __device__ __forceinline__ void run(const Params& P) {
     const int lane = threadIdx.x & 31;
-    // warps past the end redo the last tile (same values to the same addresses) instead of
-    // leaving early: no thread-dependent branch ahead of the shuffles
-    int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    warp = warp < P.n_warps ? warp : P.n_warps - 1;
+    // warps past the end redo the last tile without storing anything: no thread-dependent
+    // branch ahead of the shuffles
+    const int warp_raw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const bool dup = warp_raw >= P.n_warps;
+    const int warp = dup ? P.n_warps - 1 : warp_raw;
     const int strip = warp % P.n_strips, chunk = warp / P.n_strips;
     const int i0 = strip * P.Wu, i1 = (i0 + P.Wu < P.m) ? i0 + P.Wu : P.m;
     const int j0 = chunk * P.LJ, j1 = (j0 + P.LJ < P.n_lines) ? j0 + P.LJ : P.n_lines;
-    const int jA = j0 - NS;
-    const int own_lo = H, own_hi = H + (i1 - i0);
+    Own own;
+    {
+      const int lo = max(j0 * P.m, P.own_begin), hi = min(j1 * P.m, P.own_end);
+      own.st_lo = lo;
+      own.st_cnt = (!dup && hi > lo) ? (unsigned)(hi - lo) : 0u;
+      own.lane = (lane >= H && lane < H + (i1 - i0));
+    }
+    const bool edge_lo = P.sync.enabled && !dup && chunk < P.sync.edge_lo_chunks;
+    const bool edge_hi = P.sync.enabled && !dup && chunk >= P.sync.edge_hi_chunk0;
+    if (P.sync.enabled) {  // kernel parameter: uniform
+      wait_side(P.sync, 0, edge_lo);
+      wait_side(P.sync, 1, edge_hi);
+    }
+
     State S;
 #pragma unroll
     for (int s = 0; s < NS; ++s) S.w[s][0] = S.w[s][1] = S.w[s][2] = 0.0;
-    int g1 = jA * P.m + (i0 - H);  // first row of line jA
+    const int jA = j0 - NS;
+    int k1 = jA * P.m + (i0 - H) + lane;  // this lane's row on line jA
 #pragma unroll
-    for (int q = 0; q < PF; ++q) load(S.R[q], P, g1 + q * P.m, lane);
-    int jj = jA - 1;
+    for (int q = 0; q < PF; ++q) load(S.R[q], P, k1 + q * P.m);
     int left = P.LJ + 2 * NS;  // steps jA - 1 .. j0 + LJ + NS - 2 (a short last chunk just runs past its end)
-    while (left > 0) steps<0>(S, P, jj, g1, left, lane, j0, j1, own_lo, own_hi);
+    while (left > 0) steps<0>(S, P, k1, left, own);
+
+    if (edge_lo || edge_hi) {
+      push_rows(P, j0 * P.m + (i0 - H) + lane, j0, j1, own);
+      if (edge_lo) signal_side(P.sync, 0, lane);
+      if (edge_hi) signal_side(P.sync, 1, lane);
+    }
   }
 };
 
-template <int KIND, unsigned MASK, int NU, int PF_ = 2>
-__global__ void __launch_bounds__(128, ((popc9(MASK) <= 5 && PF_ == 2) ? 4 : 3))
+template <int KIND, unsigned MASK, int NU, int PF_, bool FAST>
+__global__ void __launch_bounds__(128, (popc9(MASK) <= 5 && PF_ == 2) ? 4 : 3)
     k_stream_leg(const __grid_constant__ Params P) {
-  Leg<KIND, MASK, NU, PF_>::run(P);
+  Leg<KIND, MASK, NU, PF_, FAST>::run(P);
 }
 
 }  // namespace sleg

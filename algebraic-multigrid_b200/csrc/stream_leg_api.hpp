@@ -1,0 +1,117 @@
+// Parameters and host-side dispatch of the register-streaming fused V-cycle legs
+// (kernels: stream_leg.cuh, compiled in legs.cu).
+#pragma once
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace amgb {
+namespace sleg {
+
+enum Kind { DOWN_U = 0, DOWN_ZERO = 1, UP = 2 };
+
+// stencil slot sl = (a + 1) * 3 + (delta + 1), ascending in column order
+constexpr unsigned kMask5 = 0x0BAu;   // (-1,0) (0,-1) (0,0) (0,1) (1,0): level 0 of an n x n grid, m = n
+constexpr unsigned kMask7a = 0x1BBu;  // level 1 with m = its smaller far offset: (-1,-1) (-1,0) (0,*) (1,0) (1,1)
+constexpr unsigned kMask7b = 0x0FEu;  // level 1 with m = its larger far offset:  (-1,0) (-1,1) (0,*) (1,-1) (1,0)
+constexpr unsigned kMask9 = 0x1FFu;   // Galerkin levels >= 2
+
+// Fused halo push of a row-block sharded level (multi-GPU): the rows of an output vector that a
+// neighbouring rank keeps as ghost rows are stored straight into that rank's copy of the vector
+// (peer-mapped pointer, the stores travel over NVLink) by the warps that produced them.
+struct Push {
+  double* dst;  // neighbour's vector, shifted so that dst[i] is the neighbour's element for my local index i
+  int begin;    // my local indices [begin, end) go to the neighbour (empty: begin >= end)
+  int end;
+};
+
+// Per-launch synchronisation with the two neighbouring ranks.  Every leg kernel of the sharded
+// cycle is a "site"; all ranks run the same sequence of sites.  side 0 = lower neighbour (rank
+// g-1), side 1 = upper neighbour.  The warps whose chunk lies next to a block edge ("edge warps")
+//   * first wait until the neighbour on that side has finished ITS edge warps of the previous
+//     site: its pushes into my ghost rows have landed (read-after-write) and it has stopped
+//     reading the ghost rows I am about to overwrite (write-after-read);
+//   * at the end push their boundary rows, fence, and count themselves done; the last one bumps
+//     this site's epoch and releases it into the neighbour's flag.
+// Epochs and counters live in device memory, so a replayed CUDA graph keeps counting.
+struct Sync {
+  int enabled;                          // 0: single GPU, nothing below is touched
+  int edge_lo_chunks;                   // chunks [0, edge_lo_chunks) are lower-edge chunks
+  int edge_hi_chunk0;                   // chunks [edge_hi_chunk0, n_chunks) are upper-edge chunks
+  int expected[2];                      // edge warps per side
+  const unsigned long long* wait_flag[2];   // my flag the neighbour raised at the previous site (nullptr: no neighbour)
+  const unsigned long long* wait_epoch[2];  // my own epoch of the previous site = the value to wait for
+  unsigned long long* epoch[2];         // this site's epoch counters
+  unsigned long long* peer_flag[2];     // the neighbour's flag for this site (nullptr: no neighbour)
+  unsigned int* done[2];                // this site's edge-warp counters (self-resetting)
+  int* timed_out;                       // set when a wait gives up (mapped host memory)
+  long long timeout_cycles;
+  Push push_u[2];                       // uout rows -> neighbours
+  Push push_fc[2];                      // fc entries (local coarse indices) -> neighbours
+};
+
+struct Params {
+  // The kernel works on a WINDOW of the level: local row k is global row base + k.  A whole level
+  // is the window [0, n) with base 0; a rank of the row-block sharded cycle passes its block plus
+  // the ghost rows on both sides (which the neighbours' previous kernels have filled) and stores
+  // results for its own rows only -- the ghost rows are recomputed redundantly, like the lanes at
+  // a warp's edge.
+  int base;       // global row of local row 0 (may be negative: rows before the level start)
+  int n_global;   // rows of the level
+  int own_begin;  // local rows [own_begin, own_end) are stored
+  int own_end;
+  int cbase;      // global coarse index of fc[0] and e[0]
+  int n_e;        // entries of e / fc that exist locally
+  int nu;         // Jacobi sweeps per smooth call (selects the kernel instantiation on the host)
+  int n;         // rows of the window
+  int m;         // line length
+  int n_lines;   // ceil(n / m)
+  int Wu;        // owned elements per warp (32 - 2H)
+  int n_strips;  // ceil(m / Wu)
+  int LJ;        // lines per chunk
+  int n_chunks;
+  int n_warps;   // n_strips * n_chunks
+  int ld;
+  int n_coarse;
+  // derived by finish() below
+  int row_lo, row_hi1;  // local rows that exist: [row_lo, row_hi1] = window ∩ level (loads are clamped to it)
+  int e_lo, e_cnt;      // local coarse indices that exist: [e_lo, e_lo + e_cnt)
+  double omega;
+  const double* val;
+  const double* vd[9];  // val + d * ld
+  const double* f;
+  const double* uin;
+  const double* e;
+  double* uout;
+  double* fc;
+  Sync sync;
+
+  // fills the derived fields; call after every other field is set
+  void finish(int n_diag) {
+    for (int d = 0; d < 9; ++d) vd[d] = val + (size_t)(d < n_diag ? d : 0) * (size_t)ld;
+    row_lo = base < 0 ? -base : 0;
+    const int hi = (n < n_global - base) ? n : n_global - base;
+    row_hi1 = hi - 1 > row_lo ? hi - 1 : row_lo;
+    e_lo = cbase < 0 ? -cbase : 0;
+    const int ehi = (n_e < n_coarse - cbase) ? n_e : n_coarse - cbase;
+    e_cnt = ehi > e_lo ? ehi - e_lo : 0;
+  }
+};
+
+__host__ __device__ constexpr int popc9(unsigned v) {
+  int c = 0;
+  for (int i = 0; i < 9; ++i) c += (v >> i) & 1u;
+  return c;
+}
+// lanes lost on each side of a warp: one per chained stencil stage (+ 1 for the restriction)
+__host__ __device__ constexpr int stages(int kind, int nu) { return kind == DOWN_U ? nu + 1 : nu; }
+__host__ __device__ constexpr int lost_lanes(int kind, int nu) { return stages(kind, nu) + (kind == UP ? 0 : 1); }
+
+// Host-side dispatch (legs.cu).  action 0: does a kernel exist for (kind, mask, nu)?  1: launch on
+// `s` (returns true when a kernel was launched).  2: set the L1 carve-out (outside stream capture)
+// and report the resident warps per SM the register count allows in *warps_per_sm.
+// fast: AMGB_ARITH_FAST kernels (FMA + refined reciprocal) instead of the reference-order ones.
+bool dispatch(int kind, unsigned mask, const Params& P, cudaStream_t s, int action, int* warps_per_sm, bool fast);
+
+}  // namespace sleg
+}  // namespace amgb

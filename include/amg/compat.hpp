@@ -10,6 +10,7 @@
 #pragma once
 #include <cmath>
 #include <cstddef>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -106,16 +107,54 @@ inline void check(int code) {
   throw std::runtime_error("amgb error " + std::to_string(code) + ": " + msg);
 }
 
-// Device mirror of a host matrix, cached by (value pointer, nnz, rows) so that repeated
-// smooth()/rss() calls with the same matrix do not upload it again.
+// Device mirror of a host matrix, cached by (value pointer, nnz, rows) AND a content
+// fingerprint that is re-evaluated on every use, so repeated smooth()/rss() calls with the same
+// matrix do not upload it again while values edited in place (coeffRef, A *= c) or a new
+// matrix allocated at a recycled address are detected and uploaded afresh -- the reference
+// always reads the live matrix.  The fingerprint hashes every index and value of matrices
+// with at most 4 M entries; above that it hashes 65536 evenly spaced entries of each array
+// (a cheap O(1) check next to the O(N) vector upload of the same call), so after editing
+// single entries of a LARGE matrix in place call AMG::invalidate_device_mirror(A).
 class MirrorCache {
   struct Entry {
     const void* key;
     long nnz;
     int rows;
+    unsigned long long fingerprint;
     amgb_matrix* m;
   };
   std::vector<Entry> entries_;
+
+  static unsigned long long mix(unsigned long long h, const void* p, std::size_t bytes) {
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    std::size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+      unsigned long long w;
+      std::memcpy(&w, c + i, 8);
+      h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+      h ^= h >> 29;
+    }
+    for (; i < bytes; ++i) h = (h ^ c[i]) * 0x100000001B3ull;
+    return h;
+  }
+  template <class Mat>
+  static unsigned long long fingerprint(const Mat& A) {
+    const std::size_t nnz = (std::size_t)A.nonZeros(), nc = (std::size_t)A.cols() + 1;
+    unsigned long long h = 0xCBF29CE484222325ull ^ (unsigned long long)nnz;
+    if (nnz <= (std::size_t(1) << 22)) {
+      h = mix(h, A.outerIndexPtr(), nc * sizeof(int));
+      h = mix(h, A.innerIndexPtr(), nnz * sizeof(int));
+      h = mix(h, A.valuePtr(), nnz * sizeof(*A.valuePtr()));
+      return h;
+    }
+    const std::size_t step = nnz / 65536, cstep = nc / 65536 + 1;
+    for (std::size_t i = 0; i < nc; i += cstep) h = mix(h, A.outerIndexPtr() + i, sizeof(int));
+    for (std::size_t i = 0; i < nnz; i += step) {
+      h = mix(h, A.innerIndexPtr() + i, sizeof(int));
+      h = mix(h, A.valuePtr() + i, sizeof(*A.valuePtr()));
+    }
+    return h;
+  }
 
  public:
   ~MirrorCache() {
@@ -124,8 +163,15 @@ class MirrorCache {
   template <class Mat>
   amgb_matrix* get(const Mat& A) {
     if (!A.isCompressed()) throw std::invalid_argument("matrix must be compressed (makeCompressed())");
-    for (auto& e : entries_)
-      if (e.key == A.valuePtr() && e.nnz == (long)A.nonZeros() && e.rows == (int)A.rows()) return e.m;
+    const unsigned long long fp = fingerprint(A);
+    for (std::size_t i = 0; i < entries_.size(); ++i) {
+      Entry& e = entries_[i];
+      if (e.key != A.valuePtr() || e.nnz != (long)A.nonZeros() || e.rows != (int)A.rows()) continue;
+      if (e.fingerprint == fp) return e.m;
+      amgb_matrix_destroy(e.m);  // same storage, different content: the mirror is stale
+      entries_.erase(entries_.begin() + (long)i);
+      break;
+    }
     amgb_matrix* m = nullptr;
     check(amgb_matrix_create((int)A.rows(), (int)A.cols(), A.outerIndexPtr(), A.innerIndexPtr(),
                              A.valuePtr(), &m));
@@ -133,8 +179,22 @@ class MirrorCache {
       amgb_matrix_destroy(entries_.front().m);
       entries_.erase(entries_.begin());
     }
-    entries_.push_back({A.valuePtr(), (long)A.nonZeros(), (int)A.rows(), m});
+    entries_.push_back({A.valuePtr(), (long)A.nonZeros(), (int)A.rows(), fp, m});
     return m;
+  }
+  // drop the mirror of A (or every mirror) explicitly
+  template <class Mat>
+  void invalidate(const Mat& A) {
+    for (std::size_t i = 0; i < entries_.size(); ++i)
+      if (entries_[i].key == A.valuePtr()) {
+        amgb_matrix_destroy(entries_[i].m);
+        entries_.erase(entries_.begin() + (long)i);
+        return;
+      }
+  }
+  void clear() {
+    for (auto& e : entries_) amgb_matrix_destroy(e.m);
+    entries_.clear();
   }
   static MirrorCache& instance() {
     static thread_local MirrorCache c;
@@ -142,4 +202,10 @@ class MirrorCache {
   }
 };
 }  // namespace detail
+
+// Call after changing the values of a large matrix in place (see MirrorCache).
+template <class Mat>
+inline void invalidate_device_mirror(const Mat& A) {
+  detail::MirrorCache::instance().invalidate(A);
+}
 }  // namespace AMG

@@ -91,6 +91,11 @@ int amgb_interp_make_operators(int64_t n_h, int64_t n_H,
  * out = R r (interpolator.hpp:64-68) and out = P e (interpolator.hpp:52-56). */
 int amgb_linear_restrict(int64_t n_h, int64_t n_H, const double* r, double* out);
 int amgb_linear_prolong(int64_t n_h, int64_t n_H, const double* e, double* out);
+/* y = A x for ANY compressed CSC matrix (n_rows x n_cols, rectangular allowed), in Eigen's
+ * evaluation order: what InterpolatorBase::restriction / prolongation compute with the stored
+ * R / P (interpolator.hpp:52-68) when they are not LinearInterpolator's operators. */
+int amgb_csc_spmv(int n_rows, int n_cols, const int* colptr, const int* rowidx, const double* val,
+                  const double* x, double* y);
 
 /* ------------------------------------------------------------------------
  * Matrix mirror + stand-alone operators (the SmootherBase::smooth boundary,
@@ -152,7 +157,16 @@ typedef struct amgb_options {
                                levels; bit 4 (default on): the small coarse levels, the
                                coarsest solve included, run in ONE kernel launch.  The
                                arithmetic, hence every bit of the result, is unchanged   */
+  int arith;                /* arithmetic of the damped-Jacobi cycle's kernels.
+                               AMGB_ARITH_REFERENCE (default): the oracle's operation order,
+                               separate multiply / subtract, IEEE division -- bit-identical
+                               to the CPU oracle.  AMGB_ARITH_FAST: fused multiply-add and
+                               u + (omega / d) * r with a Newton-refined reciprocal; results
+                               agree with the oracle to ~1e-15 relative per sweep (the
+                               north star's contract is 1e-12), iteration counts identical */
 } amgb_options;
+#define AMGB_ARITH_REFERENCE 0
+#define AMGB_ARITH_FAST 1
 void amgb_options_default(amgb_options* opt);
 
 /* Multigrid constructor (multigrid.hpp:151-244).  Validation order and the two
@@ -196,7 +210,9 @@ int64_t amgb_hierarchy_halo_exchanges_per_vcycle(const amgb_hierarchy* h);
 #define AMGB_HALO_NCCL 1
 #define AMGB_HALO_PEER 2
 int amgb_hierarchy_halo_mode(const amgb_hierarchy* h);
-/* 1 if a peer-memory exchange ever gave up waiting for a neighbour (results are invalid) */
+/* 1 if a peer-memory wait ever gave up on a neighbour (results are invalid).  amgb_vcycles,
+ * amgb_solve*, amgb_hierarchy_rss, the getters and amgb_synchronize check the same flag after
+ * their stream synchronise and fail with AMGB_ENCCL.  Timeout: ~4 s, AMGB_HALO_TIMEOUT_MS. */
 int amgb_hierarchy_halo_timed_out(amgb_hierarchy* h);
 /* host only: the plan a sharded hierarchy uses.  starts has n_levels*(world+1) slots
  * (row l holds the world+1 block boundaries of level l), the other arrays n_levels. */
@@ -220,6 +236,14 @@ int amgb_hierarchy_get_soln(amgb_hierarchy* h, int level, double* u);
 int amgb_hierarchy_get_rhs(amgb_hierarchy* h, int level, double* f);
 int amgb_hierarchy_set_soln(amgb_hierarchy* h, int level, const double* u);
 int amgb_hierarchy_set_rhs(amgb_hierarchy* h, int level, const double* f);
+/* Row-block variants for sharded hierarchies: the caller passes / receives only the rows
+ * [begin, end) of amgb_hierarchy_local_range (the whole vector when the level is not sharded).
+ * No gather: each rank moves 1/world of the bytes.  The setters are collective (they refresh
+ * the neighbours' ghost rows). */
+int amgb_hierarchy_get_soln_local(amgb_hierarchy* h, int level, double* u_block);
+int amgb_hierarchy_get_rhs_local(amgb_hierarchy* h, int level, double* f_block);
+int amgb_hierarchy_set_soln_local(amgb_hierarchy* h, int level, const double* u_block);
+int amgb_hierarchy_set_rhs_local(amgb_hierarchy* h, int level, const double* f_block);
 /* colouring per level (COLOR_GS only) */
 int amgb_hierarchy_get_coloring(const amgb_hierarchy* h, int level, int* n_colors, int* color);
 

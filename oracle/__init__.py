@@ -79,6 +79,8 @@ def lib():
         "orc_mg_create": (_p, [_p, _pd, _l, _i, _d, _l, _l, _i, _i, _d,
                                C.POINTER(_i)]),
         "orc_mg_free": (None, [_p]),
+        "orc_mg_set_smoother": (None, [_p, _i, _i, _d]),
+        "orc_mg_reset": (None, [_p]),
         "orc_mg_n_levels": (_i, [_p]),
         "orc_mg_n_dofs": (_l, [_p, _i]),
         "orc_mg_A": (_p, [_p, _i]),
@@ -294,6 +296,12 @@ class Multigrid:
 
     def vcycle(self):
         lib().orc_mg_vcycle(self.ptr)
+
+    def set_smoother(self, smoother, smoother_iters=1, omega=2.0 / 3.0):
+        lib().orc_mg_set_smoother(self.ptr, smoother, smoother_iters, omega)
+
+    def reset(self):
+        lib().orc_mg_reset(self.ptr)
 
     def rss(self):
         return lib().orc_mg_rss(self.ptr)

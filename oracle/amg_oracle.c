@@ -656,6 +656,25 @@ void orc_mg_free(orc_mg* g) {
   free(g);
 }
 
+/* Switch the smoother of an existing hierarchy (the operators do not depend on it), so one
+ * oracle hierarchy serves both the parity check and the reference-smoother timing in
+ * bench.py.  Test infrastructure, no reference counterpart. */
+void orc_mg_set_smoother(orc_mg* g, int smoother, int smoother_iters, double omega) {
+  g->smoother = smoother;
+  g->smoother_iters = smoother_iters;
+  g->omega = omega;
+  if (smoother == ORC_SMOOTHER_COLOR_GS)
+    for (int l = 0; l < g->n_levels; ++l)
+      if (!g->color[l]) {
+        g->color[l] = (int*)xmalloc(sizeof(int) * (size_t)g->n_dofs[l]);
+        g->n_colors[l] = orc_greedy_coloring(g->A[l], g->AT[l], g->color[l]);
+      }
+}
+/* u_l = 0 on every level (restart from the zero guess) */
+void orc_mg_reset(orc_mg* g) {
+  for (int l = 0; l < g->n_levels; ++l) memset(g->u[l], 0, sizeof(double) * (size_t)g->n_dofs[l]);
+}
+
 int orc_mg_n_levels(const orc_mg* g) { return g->n_levels; }
 int64_t orc_mg_n_dofs(const orc_mg* g, int l) { return g->n_dofs[l]; }
 const orc_csc* orc_mg_A(const orc_mg* g, int l) { return g->A[l]; }

@@ -2,6 +2,7 @@
 // reference's own test (jfdev001/algebraic-multigrid test/testlib.cpp:17-213) step by step,
 // with its dense Jacobi / SOR smoothers (not on the V-cycle path) replaced by the smoothers
 // this build adds.  Catch2 is not available here, so CHECK is a small macro.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -64,12 +65,73 @@ int main() {
   size_t n_from_h = AMG::Grid<double>::points_n_from_grid_spacing_h(h_from_n);
   CHECK(n_from_h == n_interior_points);
 
-  // testlib.cpp:64-71 (relaxation-parameter validation)
+  // testlib.cpp:64-71 (relaxation-parameter validation), the reference's own lines
+  double bad_omega_less_than_0 = -0.01;
+  double bad_omega_greater_than_2 = 2.01;
+  using bad_sor = AMG::SuccessiveOverRelaxation<double>;
+  CHECK_THROWS_AS(bad_sor(bad_omega_less_than_0), std::invalid_argument);
+  CHECK_THROWS_AS(bad_sor(bad_omega_greater_than_2), std::invalid_argument);
   CHECK_THROWS_AS(AMG::DampedJacobi<double>(-0.01), std::invalid_argument);
   CHECK_THROWS_AS(AMG::DampedJacobi<double>(2.01), std::invalid_argument);
 
-  // testlib.cpp:73-107: smoothers as solvers on the 4-DOF system
+  // testlib.cpp:73-115: the reference's host test smoothers (host-only classes of the mirror)
   size_t niters = 100;
+  {
+    Vec ref_jacobi_u(ndofs);
+    ref_jacobi_u.setZero();
+    AMG::Jacobi<double> ref_jacobi(niters);
+    ref_jacobi.smooth(A, ref_jacobi_u, b);
+    CHECK(ref_jacobi_u.isApprox(exact_u, ref_jacobi.tolerance));
+    Vec sor_u(ndofs);
+    sor_u.setZero();
+    AMG::SuccessiveOverRelaxation<double> sor(niters);
+    sor.smooth(A, sor_u, b);
+    CHECK(sor_u.isApprox(exact_u, sor.tolerance));
+    double tolerance = 1e-10;
+    size_t compute_error_every_n_iters = 100;
+    AMG::Jacobi<double> jacobi_base(tolerance, compute_error_every_n_iters, niters);
+    AMG::SuccessiveOverRelaxation<double> sor_base(tolerance, compute_error_every_n_iters, niters);
+    CHECK(jacobi_base.tolerance == tolerance && sor_base.n_iters == niters);
+    // the GPU driver refuses host-only smoothers
+    AMG::LinearInterpolator<double> two(2);
+    CHECK_THROWS_AS(AMG::Multigrid<double>(&two, &sor, A, b, 2, 1e-9, 1, 1), std::invalid_argument);
+  }
+
+  // stale-mirror protection: values edited in place must not hit the cached device mirror
+  {
+    Mat A2 = AMG::Grid<double>::laplacian(n_interior_points);
+    Vec zero_u(ndofs);
+    zero_u.setZero();
+    const double r_before = AMG::rss(A2, exact_u, b);
+    for (long k = 0; k < A2.nonZeros(); ++k) A2.valuePtr()[k] *= 2.0;
+    const double r_after = AMG::rss(A2, exact_u, b);  // (b - 2 A u)^2 = (b - 2 b)^2 = sum b^2
+    const double bb = AMG::rss(A2, zero_u, b);
+    CHECK(r_before < 1e-24);
+    CHECK(std::fabs(r_after - bb) <= 1e-12 * bb);
+  }
+
+  // InterpolatorBase applies the STORED operators (interpolator.hpp:52-68): replace P by 2 P
+  {
+    AMG::LinearInterpolator<double> li(2);
+    li.make_operators(7, 3, 0);
+    Vec e(3);
+    e[0] = 1.0; e[1] = -2.0; e[2] = 0.25;
+    Vec lin = li.prolongation(e, 0);
+    Mat P2 = li.get_P(0);
+    for (long k = 0; k < P2.nonZeros(); ++k) P2.valuePtr()[k] *= 2.0;
+    li.set_level_to_P(0, P2);
+    Vec twice = li.prolongation(e, 0);
+    bool ok = lin.size() == 7 && twice.size() == 7;
+    for (size_t i = 0; ok && i < 7; ++i) ok = twice[i] == 2.0 * lin[i];
+    CHECK(ok);
+    CHECK(lin[0] == 0.5 && lin[1] == 1.0 && lin[2] == -0.5 && lin[6] == 0.125);
+    Vec r(7);
+    for (size_t i = 0; i < 7; ++i) r[i] = (double)(i + 1);
+    Vec fr = li.restriction(r, 0);
+    CHECK(fr.size() == 3 && fr[0] == 0.5 * 1 + 2 + 0.5 * 3 && fr[2] == 0.5 * 5 + 6 + 0.5 * 7);
+  }
+
+  // testlib.cpp:73-107 with the smoothers this build adds, as solvers on the 4-DOF system
   Vec jacobi_u(ndofs);
   jacobi_u.setZero();
   AMG::DampedJacobi<double> jacobi(1.0, niters);

@@ -572,3 +572,146 @@ def test_properties_at_scale_4097():
     # the 5-point stencil applied to a constant: interior rows sum to zero
     mg.set_soln(0, np.ones(N0)); r = mg.residual_level(0).reshape(n, n)
     assert np.abs(r[1:-1, 1:-1]).max() <= 1e-6 * abs(A.val[2])
+
+
+def test_vcycle_4097_one_cycle_against_oracle():
+    """The benchmarked configuration itself (BASELINE configs[2]: 4097^2, 18 levels, damped Jacobi
+    2 + 2 sweeps): one V-cycle against the oracle, both arithmetic modes -- reference order must be
+    bit-identical on level 0, fast within the 1e-12 contract on every level."""
+    n, L = 4097, 18
+    sm = amg.DampedJacobi(2.0 / 3.0, 2)
+    A, b, Ao = problem(n)
+    mo = O.Multigrid(Ao, b, L, 1e-9, 1, 1, O.SMOOTHER_JACOBI, 2, 2.0 / 3.0)
+    mo.vcycle()
+    for arith in (amg.ARITH_REFERENCE, amg.ARITH_FAST):
+        mg = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1, arith=arith)
+        assert mg.fused_legs(0)
+        mg.vcycle()
+        for l in range(L):
+            assert rel(mg.get_soln(l), mo.u(l)) <= RTOL, (arith, l, rel(mg.get_soln(l), mo.u(l)))
+        if arith == amg.ARITH_REFERENCE:
+            assert mg.get_soln(0).tobytes() == mo.u(0).tobytes()
+        assert abs(mg.rss() - mo.rss()) <= RTOL * mo.rss()
+        del mg
+
+
+# ----------------------------------------------------------------- fast arithmetic (AMGB_ARITH_FAST)
+@pytest.mark.parametrize("n,L,eps,nu", [(100, 9, 1.0, 2), (129, 12, 1.0, 1), (129, 10, 1e-3, 2), (257, 13, 1.0, 2),
+                                        (513, 14, 1.0, 2), (1025, 14, 1.0, 2)])
+def test_fast_arithmetic_cycle_within_contract(n, L, eps, nu):
+    """FMA + refined-reciprocal legs: every level's iterate and right-hand side within 1e-12 of the
+    oracle after three cycles (the north star's tolerance), and not bit-identical by accident
+    (i.e. the fast kernels really ran)."""
+    sm = amg.DampedJacobi(2.0 / 3.0, nu)
+    fast, mo, _ = make_pair(n, L, sm, eps, arith=amg.ARITH_FAST)
+    assert sum(fast.fused_legs(l) for l in range(L - 1)) > 0
+    for _ in range(3):
+        fast.vcycle(); mo.vcycle()
+    worst = 0.0
+    for l in range(L):
+        worst = max(worst, rel(fast.get_soln(l), mo.u(l)), rel(fast.get_rhs(l), mo.f(l)))
+    assert worst <= RTOL, worst
+    assert abs(fast.rss() - mo.rss()) <= RTOL * mo.rss()
+
+
+def test_fast_arithmetic_iteration_count_matches_oracle():
+    sm = amg.DampedJacobi(2.0 / 3.0, 2)
+    for n, L in ((35, 8), (100, 9)):
+        fast, mo, _ = make_pair(n, L, sm, 1.0, every=5, n_iters=400, arith=amg.ARITH_FAST)
+        fast.solve(); mo.solve()
+        assert fast.iters_done == mo.iters_done
+        np.testing.assert_allclose(fast.error_history(), mo.history(), rtol=1e-9)
+
+
+# ----------------------------------------------------------------- general (non-banded) matrices: SELL-32
+def permuted_problem(n, seed):
+    """The five-point operator under a random symmetric permutation: same spectrum, but hundreds of
+    distinct diagonals, so the device mirror must take the SELL-32 layout (no DIA)."""
+    import scipy.sparse as sp
+    A = amg.Grid.laplacian(n)
+    N = n * n
+    perm = np.random.default_rng(seed).permutation(N)
+    Pm = sp.csc_matrix((np.ones(N), (np.arange(N), perm)), shape=(N, N))
+    M = (Pm @ A.to_scipy() @ Pm.T).tocsc()
+    M.sort_indices()
+    Ap = amg.CscMatrix(N, N, M.indptr, M.indices, M.data)
+    return Ap, O.Csc.from_arrays(N, N, M.indptr, M.indices, M.data), amg.Grid.rhs(n)[perm]
+
+
+@pytest.mark.parametrize("n", [24, 61])
+def test_sell_layout_operators_bit_exact(n):
+    """Residual, Jacobi, multicolour GS, level-scheduled GS and rss on a matrix that is NOT banded."""
+    Ap, Ao, b = permuted_problem(n, 5)
+    N = n * n
+    dm = amg.DeviceMatrix(Ap)
+    u = vec(N, 6)
+    assert dm.residual(u, b).tobytes() == O.residual(Ao, u, b).tobytes()
+    assert abs(dm.rss(u, b) - O.rss(Ao, u, b)) <= 1e-13 * O.rss(Ao, u, b)
+    AT = Ao.transpose()
+    want = O.jacobi_sweep(AT, O.jacobi_sweep(AT, u, b, 0.6), b, 0.6)
+    got = u.copy()
+    amg.DampedJacobi(0.6, 2).smooth(dm, got, b)
+    assert got.tobytes() == want.tobytes()
+    nc, color = O.greedy_coloring(Ao, AT)
+    nc_g, color_g = dm.coloring()
+    assert nc == nc_g and np.array_equal(color, color_g)
+    want = u.copy()
+    for c in list(range(nc)) + list(range(nc - 1, -1, -1)):
+        O.color_gs_pass(AT, color, c, b, want)
+    got = u.copy()
+    amg.MulticolorGaussSeidel(1).smooth(dm, got, b)
+    assert got.tobytes() == want.tobytes()
+    want = u.copy()
+    O.gs_forward(Ao, b, want); O.gs_backward(Ao, b, want)
+    got = u.copy()
+    amg.SparseGaussSeidel(mode=amg.GS_LEVELSCHED).smooth(dm, got, b)
+    assert got.tobytes() == want.tobytes()
+    got = u.copy()
+    amg.SparseGaussSeidel().smooth(dm, got, b)     # AUTO must fall back to the generic kernel
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("name,mk", SMOOTHERS)
+def test_sell_layout_vcycle(name, mk):
+    """A three-level V-cycle whose finest operator is in the SELL-32 layout, every level vs the oracle."""
+    n, L = 40, 3
+    Ap, Ao, b = permuted_problem(n, 7)
+    sm = mk()
+    kind = {amg.SMOOTHER_GS: O.SMOOTHER_GS, amg.SMOOTHER_JACOBI: O.SMOOTHER_JACOBI,
+            amg.SMOOTHER_COLOR_GS: O.SMOOTHER_COLOR_GS}[sm.kind]
+    mg = amg.Multigrid(amg.LinearInterpolator(L), sm, Ap, b, L, 1e-9, 1, 1)
+    mo = O.Multigrid(Ao, b, L, 1e-9, 1, 1, kind, sm.n_iters, getattr(sm, "omega", 2.0 / 3.0))
+    assert mg.format(0) == "sell"
+    for _ in range(2):
+        mg.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert rel(mg.get_soln(l), mo.u(l)) <= RTOL, (name, l)
+    assert abs(mg.rss() - mo.rss()) <= RTOL * mo.rss()
+
+
+def test_stored_interpolation_operators_are_applied():
+    """InterpolatorBase::prolongation / restriction multiply by the STORED operators
+    (interpolator.hpp:52-68), whatever they are: generic device SpMV vs the oracle."""
+    li = amg.LinearInterpolator(2)
+    li.make_operators(25, 12, 0)
+    P, R = li.get_P(0), li.get_R(0)
+    e, r = vec(12, 8), vec(25, 9)
+    Po = O.Csc.from_arrays(P.rows, P.cols, P.colptr, P.rowidx, P.val)
+    Ro = O.Csc.from_arrays(R.rows, R.cols, R.colptr, R.rowidx, R.val)
+    assert li.prolongation(e, 0).tobytes() == O.spmv(Po, e).tobytes()
+    assert li.restriction(r, 0).tobytes() == O.spmv(Ro, r).tobytes()
+    P2 = amg.CscMatrix(P.rows, P.cols, P.colptr, P.rowidx, P.val * np.linspace(1, 2, P.nnz))
+    li.set_level_to_P(0, P2)
+    P2o = O.Csc.from_arrays(P2.rows, P2.cols, P2.colptr, P2.rowidx, P2.val)
+    assert li.prolongation(e, 0).tobytes() == O.spmv(P2o, e).tobytes()
+
+
+def test_mirror_cache_sees_in_place_edits():
+    A, b, Ao = problem(35)
+    u = vec(35 * 35, 10)
+    r0 = amg.rss(A, u, b)
+    A.val *= 2.0
+    A2o = O.Csc.from_arrays(A.rows, A.cols, A.colptr, A.rowidx, A.val)
+    want = O.rss(A2o, u, b)
+    got = amg.rss(A, u, b)
+    assert abs(got - want) <= 1e-13 * want and abs(got - r0) > 1e-3 * r0
