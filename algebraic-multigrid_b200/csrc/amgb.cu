@@ -20,6 +20,7 @@
 #include "fused_leg.cuh"
 #include "galerkin_dia.cuh"
 #include "kernels.cuh"
+#include "setup_dia.cuh"
 #include "stream_leg_api.hpp"
 #include "nccl_dyn.hpp"
 
@@ -305,7 +306,17 @@ struct Operator {
     win_off = offs;
     return true;
   }
-  const DevMat& rows_of_A() const { return (symmetric || block) ? colrows : *arows; }
+  // Device-side setup: the level's rows-of-A DIA mirror was built on the GPU (setup_dia.cuh); no host
+  // matrix is kept (M / MT stay empty, the hierarchy rebuilds them on demand for the getters).
+  bool rows_primary = false;
+  void adopt_rows(DevDia&& rowsA, int n_own_rows) {
+    rows_primary = true;
+    n = n_own_rows;
+    n_mat = rowsA.n_rows;
+    colrows.is_dia = true;
+    colrows.dia = std::move(rowsA);
+  }
+  const DevMat& rows_of_A() const { return (symmetric || block || rows_primary) ? colrows : *arows; }
   const Csc& host_rows_of_A() const { return symmetric ? M : MT; }  // CSC whose column k = row k of A
 
   void ensure_fronts(cudaStream_t s) {
@@ -1115,6 +1126,7 @@ struct amgb_hierarchy {
         P.omega = opt.omega;
         P.val = W.val.p;
         P.f = S.fw.p;
+        P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", 0);
         P.finish(W.n_diag);
         return P;
       };
@@ -1170,6 +1182,7 @@ struct amgb_hierarchy {
             P.omega = opt.omega;
             P.val = A.dia.val.p;
             P.f = S.f.p;
+            P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", 0);
             P.finish(A.dia.n_diag);
             return P;
           };
@@ -1425,6 +1438,36 @@ struct amgb_hierarchy {
     CUDA_CHECK(cudaMemcpyAsync(S.f.p, full + S.s, sizeof(double) * S.n_mat, cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaStreamSynchronize(stream));
   }
+  // ---- device-side setup (setup_dia.cuh): the level-0 CSC as handed in stays on the device; the host
+  // copies of the level matrices (structural CSC, explicit zeros kept) that the getters return are
+  // rebuilt on demand with the host Galerkin chain
+  bool device_setup = false;
+  int raw_rows = 0;
+  DevBuf<int> raw_colptr, raw_rowidx;
+  DevBuf<double> raw_val;
+  std::vector<Csc> host_mats;
+  const Csc& host_matrix(int level) {
+    if (!device_setup) return ops[level]->M;
+    if (host_mats.empty()) {
+      host_mats.resize(1);
+      Csc& A = host_mats[0];
+      A.rows = A.cols = raw_rows;
+      A.colptr.resize(raw_colptr.n);
+      A.rowidx.resize(raw_rowidx.n);
+      A.val.resize(raw_val.n);
+      CUDA_CHECK(cudaMemcpy(A.colptr.data(), raw_colptr.p, raw_colptr.n * sizeof(int), cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(A.rowidx.data(), raw_rowidx.p, raw_rowidx.n * sizeof(int), cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(A.val.data(), raw_val.p, raw_val.n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    while ((int)host_mats.size() <= level) {  // multigrid.hpp:211-223
+      const int l = (int)host_mats.size();
+      Csc P = make_prolongation(n[l - 1], n[l]);
+      Csc R = transpose(P);
+      host_mats.push_back(galerkin(R, host_mats[l - 1], P));
+    }
+    return host_mats[level];
+  }
+
   DevBuf<double> gather_buf;  // full-length staging vector of the sharded getters (allocated on first use)
   void download(int l, bool want_u, double* full) {
     LevelState& S = lv[l];
@@ -1722,6 +1765,219 @@ void amgb_options_default(amgb_options* opt) {
   if (opt) options_default(opt);
 }
 
+// ---- device-side setup helpers (setup_dia.cuh) ----
+// A whole level in DIA on the device plus what the host needs to know about it.
+struct FullLevel {
+  DevDia dia;            // rows of A
+  std::vector<int> off;  // kept offsets, ascending
+};
+// Statistics of a freshly built DIA level, pruning of its empty diagonals, slice masks and the
+// DIA-vs-SELL rule of build_dia (host_setup.cpp).  Returns false when diagonal storage would stream
+// >25 % more bytes than SELL: the caller falls back to the host setup.
+static bool finalize_full_level(FullLevel& F, DevBuf<double>&& val_in, const std::vector<int>& off_in, int n, int ld,
+                                cudaStream_t s) {
+  DevBuf<double> val = std::move(val_in);
+  std::vector<int> off = off_in;
+  DevBuf<unsigned long long> count;
+  DevBuf<unsigned short> mask;
+  std::vector<unsigned long long> hc;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int nd = (int)off.size();
+    count.alloc(nd + 1);
+    count.zero(s);
+    mask.alloc(std::max(ld / 32, 1));
+    if (n > 0) LAUNCH(setup::k_dia_stats, blocks_for(ld, 256), 256, 0, s, val.p, n, ld, nd, count.p, mask.p);
+    hc.assign(nd + 1, 0);
+    CUDA_CHECK(cudaMemcpyAsync(hc.data(), count.p, (nd + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    int kept = 0;
+    for (int d = 0; d < nd; ++d) kept += hc[d] != 0;
+    if (kept == nd) break;
+    // drop the diagonals without an entry (explicit zeros only): the host layout has none either
+    DevBuf<double> packed;
+    packed.alloc((size_t)std::max(kept, 1) * ld);
+    std::vector<int> off2;
+    for (int d = 0; d < nd; ++d)
+      if (hc[d] != 0) {
+        CUDA_CHECK(cudaMemcpyAsync(packed.p + (size_t)off2.size() * ld, val.p + (size_t)d * ld, sizeof(double) * ld,
+                                   cudaMemcpyDeviceToDevice, s));
+        off2.push_back(off[d]);
+      }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    val = std::move(packed);
+    off = off2;
+  }
+  const int nd = (int)off.size();
+  int64_t nnz = 0;
+  for (int d = 0; d < nd; ++d) nnz += (int64_t)hc[d];
+  if (8.0 * nd * ld > 1.25 * 12.0 * (double)nnz + 4096.0) return false;
+  DevDia& D = F.dia;
+  D.n_rows = n;
+  D.c_min = 0;
+  D.c_max = n - 1;
+  D.ld = ld;
+  D.n_diag = nd;
+  D.nnz = nnz;
+  for (int d = 0; d < nd; ++d) D.off[d] = off[d];
+  D.live_bytes = (int64_t)nd * ld * 8;
+  const int64_t live = (int64_t)hc[nd], n_slices = ld / 32;
+  if (live * 10 <= (int64_t)nd * n_slices * 9) {  // skipping empty slices saves >= a tenth of the matrix bytes
+    D.mask = std::move(mask);
+    D.live_bytes = n_slices * 2 + 256ll * live;
+  }
+  D.val = std::move(val);
+  F.off = off;
+  return true;
+}
+// Rows [row_begin, row_begin + n_dst) of a whole-level DIA with local numbering (rows outside the
+// level stay empty); with_stats: also the slice masks and entry count (the per-operator kernels use them).
+static void slice_level(const FullLevel& F, int n_src, int row_begin, int n_dst, DevDia& out, bool with_stats,
+                        cudaStream_t s) {
+  const int nd = F.dia.n_diag;
+  const int ld = (n_dst + 31) / 32 * 32;
+  out.val.alloc((size_t)std::max(nd, 1) * std::max(ld, 32));
+  out.val.zero(s);
+  if (n_dst > 0)
+    LAUNCH(setup::k_dia_slice, blocks_for(n_dst, 256), 256, 0, s, F.dia.val.p, n_src, F.dia.ld, nd, row_begin, out.val.p,
+           n_dst, ld);
+  out.n_rows = n_dst;
+  out.c_min = 0;
+  out.c_max = n_src - 1;
+  out.ld = ld;
+  out.n_diag = nd;
+  for (int d = 0; d < nd; ++d) out.off[d] = F.dia.off[d];
+  out.live_bytes = (int64_t)nd * ld * 8;
+  out.nnz = 0;
+  if (with_stats && n_dst > 0) {
+    DevBuf<unsigned long long> count;
+    count.alloc(nd + 1);
+    count.zero(s);
+    DevBuf<unsigned short> mask;
+    mask.alloc(std::max(ld / 32, 1));
+    LAUNCH(setup::k_dia_stats, blocks_for(ld, 256), 256, 0, s, out.val.p, n_dst, ld, nd, count.p, mask.p);
+    std::vector<unsigned long long> hc(nd + 1, 0);
+    CUDA_CHECK(cudaMemcpyAsync(hc.data(), count.p, (nd + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int d = 0; d < nd; ++d) out.nnz += (int64_t)hc[d];
+    const int64_t live = (int64_t)hc[nd], n_slices = ld / 32;
+    if (live * 10 <= (int64_t)nd * n_slices * 9) {
+      out.mask = std::move(mask);
+      out.live_bytes = n_slices * 2 + 256ll * live;
+    }
+  }
+}
+// The whole hierarchy on the device: level 0 from the raw CSC arrays, levels >= 1 by Galerkin products.
+// false: the operator (or one of its coarse operators) does not fit the DIA layout -> host setup.
+static bool device_build_levels(amgb_hierarchy* h, int n_rows, const int* colptr, const int* rowidx, const double* val,
+                                std::vector<FullLevel>& full) {
+  cudaStream_t s = h->stream;
+  const int L = h->L;
+  const int64_t nnz = colptr[n_rows];
+  if (n_rows < 1 || nnz < 1) return false;
+  h->raw_rows = n_rows;
+  h->raw_colptr.upload(colptr, (size_t)n_rows + 1, s);
+  h->raw_rowidx.upload(rowidx, (size_t)nnz, s);
+  h->raw_val.upload(val, (size_t)nnz, s);
+  // distinct offsets
+  const int shift = n_rows - 1;
+  const int n_words = (2 * n_rows - 1 + 31) / 32;
+  DevBuf<unsigned> bitmap;
+  bitmap.alloc(n_words);
+  bitmap.zero(s);
+  DevBuf<int> list;
+  list.alloc(2 + setup::kMaxOffsets);
+  list.zero(s);
+  LAUNCH(setup::k_mark_offsets, blocks_for(n_rows, 256), 256, 0, s, h->raw_colptr.p, h->raw_rowidx.p, n_rows, shift,
+         bitmap.p);
+  LAUNCH(setup::k_collect_offsets, blocks_for(n_words, 256), 256, 0, s, bitmap.p, n_words, shift, setup::kMaxOffsets,
+         list.p);
+  std::vector<int> hl(2 + setup::kMaxOffsets, 0);
+  CUDA_CHECK(cudaMemcpyAsync(hl.data(), list.p, hl.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (hl[0] < 1 || hl[0] > setup::kMaxOffsets) return false;
+  std::vector<int> off(hl.begin() + 1, hl.begin() + 1 + hl[0]);
+  std::sort(off.begin(), off.end());
+  auto pack = [](const std::vector<int>& v) {
+    setup::Offsets o{};
+    o.n = (int)v.size();
+    for (int d = 0; d < o.n; ++d) o.v[d] = v[d];
+    return o;
+  };
+  // DIA of "row c = CSC column c" (rows of A^T), then rows of A (the same array when A is bitwise symmetric)
+  const int ld0 = (n_rows + 31) / 32 * 32;
+  DevBuf<double> colrows;
+  colrows.alloc((size_t)off.size() * ld0);
+  colrows.zero(s);
+  LAUNCH(setup::k_csc_to_dia, blocks_for(n_rows, 256), 256, 0, s, h->raw_colptr.p, h->raw_rowidx.p, h->raw_val.p, n_rows,
+         pack(off), colrows.p, ld0);
+  DevBuf<int> flag;
+  flag.alloc(1);
+  flag.zero(s);
+  LAUNCH(setup::k_dia_asymmetric, blocks_for(n_rows, 256), 256, 0, s, colrows.p, n_rows, ld0, pack(off), flag.p);
+  int asym = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&asym, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  full.clear();
+  full.resize(L);
+  if (asym) {
+    std::vector<int> off_t;
+    for (auto it = off.rbegin(); it != off.rend(); ++it) off_t.push_back(-*it);
+    DevBuf<double> rowsA;
+    rowsA.alloc((size_t)off_t.size() * ld0);
+    rowsA.zero(s);
+    LAUNCH(setup::k_dia_transpose, blocks_for(n_rows, 256), 256, 0, s, colrows.p, n_rows, ld0, pack(off), pack(off_t),
+           rowsA.p);
+    if (!finalize_full_level(full[0], std::move(rowsA), off_t, n_rows, ld0, s)) return false;
+  } else {
+    if (!finalize_full_level(full[0], std::move(colrows), off, n_rows, ld0, s)) return false;
+  }
+  // coarse levels: A_{l+1} = R (A_l P), one thread per coarse row (multigrid.hpp:219-223)
+  for (int l = 1; l < L; ++l) {
+    const int n_f = (int)h->n[l - 1], n_c = (int)h->n[l];
+    const DevDia& Fd = full[l - 1].dia;
+    gal::FineDia A;
+    A.n = n_f;
+    A.nd = Fd.n_diag;
+    A.ld = Fd.ld;
+    for (int d = 0; d < A.nd; ++d) A.off[d] = Fd.off[d];
+    A.val = Fd.val.p;
+    CoarseOffsets oc{};
+    const int nd_c = gal::coarse_offsets(A.nd, A.off, oc.v);
+    if (nd_c < 1) return false;
+    const int ld_c = (n_c + 31) / 32 * 32;
+    DevBuf<double> out;
+    out.alloc((size_t)nd_c * ld_c);
+    out.zero(s);
+    LAUNCH(k_galerkin_dia, blocks_for(n_c, 256), 256, 0, s, A, n_c, nd_c, oc, out.p, ld_c);
+    std::vector<int> off_c(oc.v, oc.v + nd_c);
+    if (!finalize_full_level(full[l], std::move(out), off_c, n_c, ld_c, s)) return false;
+  }
+  return true;
+}
+// host CSC (rows of A, explicit zeros already dropped) of a small device DIA level: the coarsest factorisation
+static Csc csc_from_device_dia(const DevDia& D, cudaStream_t s) {
+  std::vector<double> v((size_t)D.n_diag * D.ld);
+  CUDA_CHECK(cudaMemcpyAsync(v.data(), D.val.p, v.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  // assemble row by row (column k of M = row k of A), then transpose: the factorisation reads the lower
+  // triangle A(r, c), r >= c, exactly like the host path does for operators symmetric only up to rounding
+  Csc M;
+  M.rows = M.cols = D.n_rows;
+  M.colptr.assign((size_t)D.n_rows + 1, 0);
+  for (int r = 0; r < D.n_rows; ++r) {
+    for (int d = 0; d < D.n_diag; ++d) {
+      const double a = v[(size_t)d * D.ld + r];
+      const int c = r + D.off[d];
+      if (a != 0.0 && c >= 0 && c < D.n_rows) {
+        M.rowidx.push_back(c);
+        M.val.push_back(a);
+      }
+    }
+    M.colptr[(size_t)r + 1] = (int)M.rowidx.size();
+  }
+  return transpose(M);  // columns of A, like the host path's mats[L - 1]
+}
+
 static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_rows, int n_cols,
                              const int* colptr, const int* rowidx, const double* val, const double* b,
                              int64_t b_rows, const amgb_options* opt_in, amgb_hierarchy** out) {
@@ -1738,6 +1994,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
   if (o.n_levels < 1) throw std::invalid_argument("n_levels must be >= 1");
   if (n_rows != n_cols) throw std::invalid_argument("A must be square");
   if (o.smoother < 0 || o.smoother > 2) throw std::invalid_argument("unknown smoother kind");
+  if (o.arith != AMGB_ARITH_REFERENCE && o.arith != AMGB_ARITH_FAST) throw std::invalid_argument("unknown arithmetic mode");
   if (!b || !rowidx || !val) throw std::invalid_argument("null argument");
   require_device();
 
@@ -1751,34 +2008,68 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
   cudaStream_t s = h->stream;
   const int L = h->L;
 
-  // ---- host hierarchy (multigrid.hpp:190-223): every rank builds all of it ----
-  std::vector<Csc> mats(L);
-  mats[0] = csc_from_arrays(n_rows, n_cols, colptr, rowidx, val);
+  // ---- level sizes (multigrid.hpp:127-130, :213-215) ----
   h->n.resize(L);
   h->n[0] = n_rows;
   for (int l = 1; l < L; ++l) {
-    const int64_t nh = h->n[l - 1];
-    const int64_t nH = coarse_dofs(nh);
-    if (nH < 1) throw std::invalid_argument("too many levels: level " + std::to_string(l) + " is empty");
-    Csc P = make_prolongation(nh, nH);
-    Csc R = transpose(P);
-    mats[l] = galerkin(R, mats[l - 1], P);
-    h->n[l] = nH;
+    h->n[l] = coarse_dofs(h->n[l - 1]);
+    if (h->n[l] < 1) throw std::invalid_argument("too many levels: level " + std::to_string(l) + " is empty");
+  }
+
+  // ---- the level operators (multigrid.hpp:190-223) ----
+  // Damped-Jacobi cycles on banded operators: built on the DEVICE from the raw CSC arrays
+  // (setup_dia.cuh); every rank builds the whole (cheap) hierarchy and slices its row blocks.
+  // Everything else (Gauss-Seidel schedules and colourings need the host matrices; unstructured
+  // operators need SELL): host setup, every rank builds all of it.  AMGB_HOST_SETUP=1 forces the latter.
+  std::vector<FullLevel> full;
+  std::vector<Csc> mats;
+  const char* force_host = std::getenv("AMGB_HOST_SETUP");
+  if (o.smoother == AMGB_SMOOTHER_JACOBI && !(force_host && std::string(force_host) == "1"))
+    h->device_setup = device_build_levels(h.get(), n_rows, colptr, rowidx, val, full);
+  if (!h->device_setup) {
+    full.clear();
+    h->raw_colptr.release();
+    h->raw_rowidx.release();
+    h->raw_val.release();
+    mats.resize(L);
+    mats[0] = csc_from_arrays(n_rows, n_cols, colptr, rowidx, val);
+    for (int l = 1; l < L; ++l) {
+      Csc P = make_prolongation(h->n[l - 1], h->n[l]);
+      Csc R = transpose(P);
+      mats[l] = galerkin(R, mats[l - 1], P);
+    }
+  }
+  // offsets (col - row of the non-zero entries) of every level, at most 17 kept: half-bandwidths and
+  // the line structure the streaming legs need
+  std::vector<std::vector<int>> level_off(L);
+  std::vector<int> half_bw(L, 0);
+  for (int l = 0; l < L; ++l) {
+    if (h->device_setup) {
+      level_off[l] = full[l].off;
+    } else {
+      const Csc& M = mats[l];
+      std::vector<int>& offs = level_off[l];
+      for (int c = 0; c < M.cols; ++c)
+        for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p) {
+          if (M.val[p] == 0.0) continue;
+          const int off = M.rowidx[p] - c;
+          half_bw[l] = std::max(half_bw[l], std::abs(off));
+          if (offs.size() > 16) continue;
+          auto it = std::lower_bound(offs.begin(), offs.end(), off);
+          if (it == offs.end() || *it != off) offs.insert(it, off);
+        }
+    }
+    for (int off : level_off[l]) half_bw[l] = std::max(half_bw[l], std::abs(off));
   }
   // coarsest factorisation (multigrid.hpp:240-243); the direct solve is a banded
   // substitution in one block, so refuse hierarchies whose coarsest level is not small
-  std::vector<int> half_bw(L, 0);
-  for (int l = 0; l < L; ++l)
-    for (int c = 0; c < mats[l].cols; ++c)
-      for (int p = mats[l].colptr[c]; p < mats[l].colptr[c + 1]; ++p)
-        if (mats[l].val[p] != 0.0) half_bw[l] = std::max(half_bw[l], std::abs(mats[l].rowidx[p] - c));
   {
     const int64_t nc = h->n[L - 1], bw = std::max(half_bw[L - 1], 1);
     if ((double)nc * bw * bw > 2e10 || nc * bw > (1ll << 27))
       throw std::invalid_argument("coarsest level too large for the direct solve (" + std::to_string(nc) +
                                   " DOF, half-bandwidth " + std::to_string(bw) + "): use more levels");
   }
-  h->factor = factor_banded_ldlt(mats[L - 1]);
+  h->factor = h->device_setup ? factor_banded_ldlt(csc_from_device_dia(full[L - 1].dia, s)) : factor_banded_ldlt(mats[L - 1]);
 
   // ---- partition (sharded runs only) ----
   const int world = comm ? comm->world : 1;
@@ -1793,23 +2084,8 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
     if ((o.fuse & 4) && (o.smoother_iters == 1 || o.smoother_iters == 2)) {
       max_sharded = 0;
       for (int l = 0; l + 1 < L; ++l) {
-        const Csc& M = mats[l];
-        std::vector<int> offs;
-        bool banded = true;
-        for (int c = 0; c < M.cols && banded; ++c)
-          for (int p = M.colptr[c]; p < M.colptr[c + 1]; ++p) {
-            if (M.val[p] == 0.0) continue;
-            const int off = M.rowidx[p] - c;
-            auto it = std::lower_bound(offs.begin(), offs.end(), off);
-            if (it == offs.end() || *it != off) {
-              if ((int)offs.size() == 10) {
-                banded = false;
-                break;
-              }
-              offs.insert(it, off);
-            }
-          }
-        if (!banded || offs.empty()) break;
+        const std::vector<int>& offs = level_off[l];
+        if (offs.empty() || offs.size() > 10) break;
         leg::Plan st = leg::plan_leg(leg::UP, 2, (int)h->n[l], (int)offs.size(), offs.data(), 148, 200 * 1024);
         if (!st.ok || !(st.P.m < st.P.n) || st.P.rho != 1) break;
         unsigned mask = 0;
@@ -1836,6 +2112,8 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
     LevelState& S = h->lv[l];
     S.n_global = h->n[l];
     h->ops[l].reset(new Operator());
+    const bool want_window =
+        (o.fuse & 4) && o.smoother == AMGB_SMOOTHER_JACOBI && (o.smoother_iters == 1 || o.smoother_iters == 2);
     if (l < h->n_sharded) {
       S.sharded = true;
       S.s = h->plan.start[l][g];
@@ -1844,12 +2122,30 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
       S.halo_hi = h->plan.halo_hi[l];
       S.n_own = (int)(S.e - S.s);
       S.n_mat = (int)std::min<int64_t>(S.n_own + h->plan.ghost[l], h->n[l] - S.s);
-      h->ops[l]->build_block(std::move(mats[l]), (int)S.s, S.n_mat, S.n_own, S.halo_lo, S.halo_hi, s);
+      if (h->device_setup) {
+        // row block (+ ghost rows) and window of this rank, sliced out of the whole level on the device
+        DevDia blk;
+        slice_level(full[l], (int)h->n[l], (int)S.s, S.n_mat, blk, true, s);
+        blk.c_min = -S.halo_lo;
+        blk.c_max = S.n_own + S.halo_hi - 1;
+        h->ops[l]->adopt_rows(std::move(blk), S.n_own);
+        h->ops[l]->block = true;
+        if (want_window) {
+          slice_level(full[l], (int)h->n[l], (int)(S.s - S.halo_lo), (int)S.n_vec(), h->ops[l]->win, false, s);
+          h->ops[l]->win_off = full[l].off;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        full[l].dia.val.release();  // the whole-level copy is not needed any more
+        full[l].dia.mask.release();
+      } else {
+        h->ops[l]->build_block(std::move(mats[l]), (int)S.s, S.n_mat, S.n_own, S.halo_lo, S.halo_hi, s);
+      }
     } else {
       S.s = 0;
       S.e = h->n[l];
       S.n_own = S.n_mat = (int)h->n[l];
-      h->ops[l]->build(std::move(mats[l]), s);
+      if (h->device_setup) h->ops[l]->adopt_rows(std::move(full[l].dia), S.n_own);
+      else h->ops[l]->build(std::move(mats[l]), s);
     }
     // +8: the fused legs copy 16-byte aligned windows, which may reach one entry past the end
     S.u.alloc(S.n_vec() + 8);
@@ -1864,8 +2160,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
       S.fw.alloc(S.n_vec() + 8);
       S.fw.zero(s);
       // window mirror of the operator for the fused legs (block + ghost rows on both sides)
-      if ((o.fuse & 4) && o.smoother == AMGB_SMOOTHER_JACOBI && (o.smoother_iters == 1 || o.smoother_iters == 2))
-        h->ops[l]->build_window((int)(S.s - S.halo_lo), (int)S.n_vec(), s);
+      if (want_window && !h->device_setup) h->ops[l]->build_window((int)(S.s - S.halo_lo), (int)S.n_vec(), s);
     }
     if (!(l + 1 == L && o.skip_dead_coarse_smooth)) h->prepare_smoother(l);
   }
@@ -2010,7 +2305,12 @@ int64_t amgb_hierarchy_n_dofs(const amgb_hierarchy* h, int level) {
   return (h && level >= 0 && level < h->L) ? h->n[level] : -1;
 }
 int64_t amgb_hierarchy_nnz(const amgb_hierarchy* h, int level) {
-  return (h && level >= 0 && level < h->L) ? h->ops[level]->M.nnz() : -1;
+  if (!h || level < 0 || level >= h->L) return -1;
+  try {
+    return const_cast<amgb_hierarchy*>(h)->host_matrix(level).nnz();
+  } catch (...) {
+    return -1;
+  }
 }
 int64_t amgb_hierarchy_nnz_device(const amgb_hierarchy* h, int level) {
   return (h && level >= 0 && level < h->L) ? h->ops[level]->nnz_device() : -1;
@@ -2020,7 +2320,7 @@ int amgb_hierarchy_get_matrix(const amgb_hierarchy* h, int level, int* colptr, i
   return guarded([&] {
     if (!h) throw std::invalid_argument("null argument");
     h->check_level(level);
-    const Csc& M = h->ops[level]->M;
+    const Csc& M = const_cast<amgb_hierarchy*>(h)->host_matrix(level);
     if (colptr) std::memcpy(colptr, M.colptr.data(), M.colptr.size() * sizeof(int));
     if (rowidx) std::memcpy(rowidx, M.rowidx.data(), M.rowidx.size() * sizeof(int));
     if (val) std::memcpy(val, M.val.data(), M.val.size() * sizeof(double));
@@ -2400,31 +2700,37 @@ int amgb_hierarchy_galerkin_device(amgb_hierarchy* h, int level, double* ms_out,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (ms_out) *ms_out = ms;
-    // compare with the host-built mirror of level + 1, diagonal by diagonal
-    std::vector<double> got((size_t)nd_c * ld_c), want((size_t)Cm.dia.n_diag * Cm.dia.ld);
+    // compare with the HOST Galerkin product of level + 1 (rows of A in DIA, built from the host
+    // chain -- in device-setup mode that chain is rebuilt here on demand), diagonal by diagonal, and
+    // with the mirror of level + 1 the hierarchy actually uses
+    const Csc& Mh = h->host_matrix(level + 1);
+    Csc MhT = transpose(Mh);
+    Dia want_d = build_dia(bitwise_equal(Mh, MhT) ? Mh : MhT);
+    if (!want_d.ok) throw ApiError(AMGB_ESTATE, "host coarse operator does not fit the DIA layout");
+    std::vector<double> got((size_t)nd_c * ld_c), used((size_t)Cm.dia.n_diag * Cm.dia.ld);
     CUDA_CHECK(cudaMemcpy(got.data(), out.p, got.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    CUDA_CHECK(cudaMemcpy(want.data(), Cm.dia.val.p, want.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(used.data(), Cm.dia.val.p, used.size() * sizeof(double), cudaMemcpyDeviceToHost));
     int64_t bad = 0;
     std::vector<char> matched(nd_c, 0);
-    for (int d = 0; d < Cm.dia.n_diag; ++d) {
-      int c = -1;
+    for (int d = 0; d < want_d.n_diag; ++d) {
+      int c = -1, u = -1;
       for (int k = 0; k < nd_c; ++k)
-        if (oc.v[k] == Cm.dia.off[d]) c = k;
-      if (c < 0) {
+        if (oc.v[k] == want_d.off[d]) c = k;
+      for (int k = 0; k < Cm.dia.n_diag; ++k)
+        if (Cm.dia.off[k] == want_d.off[d]) u = k;
+      if (c < 0 || u < 0) {
         bad += n_c;
         continue;
       }
       matched[c] = 1;
-      bad += std::memcmp(&got[(size_t)c * ld_c], &want[(size_t)d * Cm.dia.ld], sizeof(double) * n_c) != 0
-                 ? [&] {
-                     int64_t k = 0;
-                     for (int i = 0; i < n_c; ++i)
-                       k += std::memcmp(&got[(size_t)c * ld_c + i], &want[(size_t)d * Cm.dia.ld + i], 8) != 0;
-                     return k;
-                   }()
-                 : 0;
+      for (int i = 0; i < n_c; ++i) {
+        const double w = want_d.val[(size_t)d * want_d.ld + i];
+        bad += std::memcmp(&got[(size_t)c * ld_c + i], &w, 8) != 0;
+        bad += std::memcmp(&used[(size_t)u * Cm.dia.ld + i], &w, 8) != 0;
+      }
     }
-    for (int c = 0; c < nd_c; ++c)  // diagonals the host mirror does not have must be all zero
+    if (Cm.dia.n_diag != want_d.n_diag) bad += n_c;
+    for (int c = 0; c < nd_c; ++c)  // diagonals the host operator does not have must be all zero
       if (!matched[c])
         for (int i = 0; i < n_c; ++i) bad += (got[(size_t)c * ld_c + i] != 0.0);
     if (mismatches) *mismatches = bad;

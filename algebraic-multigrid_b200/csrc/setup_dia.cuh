@@ -1,0 +1,129 @@
+// Device-side hierarchy setup on the diagonal (DIA) layout (reference:
+// the Multigrid constructor, include/amg/multigrid.hpp:190-243).  The level-0 operator arrives as
+// the raw CSC arrays of an Eigen::SparseMatrix; everything from there on -- conversion to DIA,
+// symmetry check / transposition, the Galerkin products A_{l+1} = R (A_l P) (galerkin_dia.cuh),
+// pruning of empty diagonals, slice masks, row-block and window mirrors of sharded levels -- runs
+// on the GPU, so the host never touches the O(nnz) data.  Values are bit-identical to the host
+// setup (host_setup.cpp) because k_galerkin_dia evaluates every entry in Eigen's order.
+#pragma once
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace amgb {
+namespace setup {
+
+constexpr int kMaxOffsets = 16;
+struct Offsets {
+  int n;
+  int v[kMaxOffsets];
+};
+
+// ---- distinct offsets rowidx[p] - column of a CSC matrix: bitmap over [-(n_rows-1), n_cols-1] ----
+__global__ void __launch_bounds__(256) k_mark_offsets(const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                                                      int n_cols, int shift, unsigned* bitmap) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+    const unsigned o = (unsigned)(rowidx[p] - c + shift);
+    const unsigned bit = 1u << (o & 31u);
+    if (!(bitmap[o >> 5] & bit)) atomicOr(bitmap + (o >> 5), bit);  // a handful of words: mostly cached reads
+  }
+}
+// list[0] = count (may exceed cap: too many diagonals), list[1 + i] = offsets in no particular order
+__global__ void __launch_bounds__(256) k_collect_offsets(const unsigned* __restrict__ bitmap, int n_words, int shift,
+                                                         int cap, int* list) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  unsigned bits = bitmap[w];
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int slot = atomicAdd(list, 1);
+    if (slot < cap) list[1 + slot] = w * 32 + b - shift;
+  }
+}
+
+// ---- CSC -> DIA of "row c = CSC column c" (smoother.hpp:101-117); val pre-zeroed ----
+__global__ void __launch_bounds__(256) k_csc_to_dia(const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                                                    const double* __restrict__ val, int n_cols, Offsets off,
+                                                    double* __restrict__ dia, int ld) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+    const int o = rowidx[p] - c;
+#pragma unroll
+    for (int d = 0; d < kMaxOffsets; ++d)
+      if (d < off.n && off.v[d] == o) dia[(size_t)d * ld + c] = val[p];
+  }
+}
+
+// ---- bitwise symmetry of a square DIA operator: A(r, r+o) == A(r+o, r) ----
+__global__ void __launch_bounds__(256) k_dia_asymmetric(const double* __restrict__ dia, int n, int ld, Offsets off,
+                                                        int* flag) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int d = 0; d < off.n; ++d) {
+    const double a = dia[(size_t)d * ld + r];
+    const int c = r + off.v[d];
+    if (c < 0 || c >= n) {
+      if (a != 0.0) *flag = 1;
+      continue;
+    }
+    double b = 0.0;
+    for (int e = 0; e < off.n; ++e)
+      if (off.v[e] == -off.v[d]) b = dia[(size_t)e * ld + c];
+    if (__double_as_longlong(a) != __double_as_longlong(b) && !(a == 0.0 && b == 0.0)) *flag = 1;
+  }
+}
+// dst = transpose: dst(r + o, diagonal of -o) = src(r, diagonal of o); off_t lists the negated offsets ascending
+__global__ void __launch_bounds__(256) k_dia_transpose(const double* __restrict__ src, int n, int ld, Offsets off,
+                                                       Offsets off_t, double* __restrict__ dst) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int d = 0; d < off.n; ++d) {
+    const int c = r + off.v[d];
+    if (c < 0 || c >= n) continue;
+    for (int e = 0; e < off_t.n; ++e)
+      if (off_t.v[e] == -off.v[d]) dst[(size_t)e * ld + c] = src[(size_t)d * ld + r];
+  }
+}
+
+// ---- statistics: entries per diagonal, and the per-slice occupancy mask (bit d of mask[s] set when
+// diagonal d has an entry among rows [32 s, 32 s + 32)), live = number of (slice, diagonal) pairs set
+__global__ void __launch_bounds__(256) k_dia_stats(const double* __restrict__ dia, int n, int ld, int nd,
+                                                   unsigned long long* count /* nd + 1 */, unsigned short* mask) {
+  __shared__ unsigned int sh[kMaxOffsets + 1];
+  if (threadIdx.x <= kMaxOffsets) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  unsigned m = 0;
+  for (int d = 0; d < nd; ++d) {
+    const bool nz = (r < n) && dia[(size_t)d * ld + r] != 0.0;
+    const unsigned b = __ballot_sync(0xffffffffu, nz);
+    if (b) m |= 1u << d;
+    if (lane == 0 && b) {
+      atomicAdd(&sh[d], __popc(b));
+      atomicAdd(&sh[kMaxOffsets], 1u);
+    }
+  }
+  if (lane == 0 && (r >> 5) < (ld >> 5)) mask[r >> 5] = (unsigned short)m;
+  __syncthreads();
+  if (threadIdx.x < nd && sh[threadIdx.x]) atomicAdd(count + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
+  if (threadIdx.x == kMaxOffsets && sh[kMaxOffsets]) atomicAdd(count + nd, (unsigned long long)sh[kMaxOffsets]);
+}
+
+// ---- rows [row_begin, row_begin + n_dst) of a DIA operator with local numbering; rows outside
+// [0, n_src) stay empty (dst pre-zeroed) ----
+__global__ void __launch_bounds__(256) k_dia_slice(const double* __restrict__ src, int n_src, int ld_src, int nd,
+                                                   int row_begin, double* __restrict__ dst, int n_dst, int ld_dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_dst) return;
+  const int r = row_begin + t;
+  if (r < 0 || r >= n_src) return;
+  for (int d = 0; d < nd; ++d) dst[(size_t)d * ld_dst + t] = src[(size_t)d * ld_src + r];
+}
+
+}  // namespace setup
+}  // namespace amgb

@@ -114,6 +114,16 @@ struct Leg {
     }
   }
 
+  // L2 prefetch of the operator / f / input rows of a line further ahead than the register ring:
+  // no registers, the later LDG then hits L2 (lower latency = fewer lines needed in flight)
+  static __device__ __forceinline__ void prefetch(const Params& P, int k) {
+    const int kc = min(max(k, P.row_lo), P.row_hi1);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.vd[d] + kc));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.f + kc));
+    if (KIND != DOWN_ZERO) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.uin + kc));
+  }
+
   // input value of a row (stage 0); kg = global row
   static __device__ __forceinline__ double input(const Line& L, const Params& P, int kg) {
     if (KIND == DOWN_U) return L.u;
@@ -199,6 +209,7 @@ struct Leg {
   static __device__ __forceinline__ void step(State& S, const Params& P, int k1, const Own& own) {
     const int m = P.m;
     load(S.R[(P_ + PF) % RS], P, k1 + PF * m);
+    if (P.l2_ahead > 0) prefetch(P, k1 + (PF + P.l2_ahead) * m);
     // ---- input stage, line jj + 1
     {
       const Line& L = S.R[P_ % RS];

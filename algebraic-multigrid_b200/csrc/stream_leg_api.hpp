@@ -76,6 +76,7 @@ struct Params {
   // derived by finish() below
   int row_lo, row_hi1;  // local rows that exist: [row_lo, row_hi1] = window ∩ level (loads are clamped to it)
   int e_lo, e_cnt;      // local coarse indices that exist: [e_lo, e_lo + e_cnt)
+  int l2_ahead;         // > 0: prefetch the line this many steps beyond the register ring into L2
   double omega;
   const double* val;
   const double* vd[9];  // val + d * ld
