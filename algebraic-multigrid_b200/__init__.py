@@ -125,6 +125,7 @@ SIGNATURES = {
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
     "amgb_hierarchy_fused_legs": (_i, [_p, _i]),
     "amgb_hierarchy_tail_first": (_i, [_p]),
+    "amgb_hierarchy_mid_range": (_i, [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "amgb_hierarchy_galerkin_device": (_i, [_p, _i, C.POINTER(_d), C.POINTER(_l)]),
     "amgb_hierarchy_leg_plan": (_i, [_p, _i, _i, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "amgb_hierarchy_pass_bytes": (_l, [_p, _i]),
@@ -689,6 +690,12 @@ class Multigrid:
     def tail_first(self):
         """First level of the coarse tail that runs in one launch (-1: none)."""
         return lib().amgb_hierarchy_tail_first(self.h)
+
+    def mid_range(self):
+        """(first, end, tile rows, blocks) of the levels the two mid-level kernels cover; first = -1: none."""
+        a, b, t, nb = _i(), _i(), _i(), _i()
+        _check(lib().amgb_hierarchy_mid_range(self.h, C.byref(a), C.byref(b), C.byref(t), C.byref(nb)))
+        return a.value, b.value, t.value, nb.value
 
     def leg_plan(self, level, up=False):
         info = np.zeros(10, np.int64)

@@ -20,6 +20,7 @@
 #include "fused_leg.cuh"
 #include "galerkin_dia.cuh"
 #include "kernels.cuh"
+#include "mid_levels.cuh"
 #include "setup_dia.cuh"
 #include "stream_leg_api.hpp"
 #include "nccl_dyn.hpp"
@@ -596,7 +597,7 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
-  o->fuse = 1 | 4 | 16;  // zero-guess sweep, streaming legs, coarse tail; prolongation fusion (bit 1) measured slower
+  o->fuse = 1 | 4 | 16 | 32;  // zero-guess sweep, streaming legs, coarse tail, mid levels; prolongation fusion (bit 1) measured slower
   o->arith = AMGB_ARITH_REFERENCE;
 }
 
@@ -1126,7 +1127,9 @@ struct amgb_hierarchy {
         P.omega = opt.omega;
         P.val = W.val.p;
         P.f = S.fw.p;
-        P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", 0);
+        // L2 prefetch two lines beyond the register ring pays on the HBM-bound levels (measured:
+        // level 0 down leg 231 -> 197 us, profiles/r2_stream_legs.md) and costs issue slots below
+        P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", S.n_vec() >= (1 << 21) ? 2 : 0);
         P.finish(W.n_diag);
         return P;
       };
@@ -1182,7 +1185,9 @@ struct amgb_hierarchy {
             P.omega = opt.omega;
             P.val = A.dia.val.p;
             P.f = S.f.p;
-            P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", 0);
+            // L2 prefetch two lines beyond the register ring pays on the HBM-bound levels (measured:
+            // level 0 down leg 231 -> 197 us, profiles/r2_stream_legs.md) and costs issue slots below
+            P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", n[l] >= (1 << 21) ? 2 : 0);
             P.finish(A.dia.n_diag);
             return P;
           };
@@ -1300,11 +1305,87 @@ struct amgb_hierarchy {
     tail_first = first;
   }
 
+  // ---- mid levels (mid_levels.cuh): levels [mid_first, mid_end) of a damped-Jacobi cycle, all their
+  // down legs in ONE launch and all their up legs in another (option fuse bit 5)
+  int mid_first = -1, mid_end = -1;
+  mid::Params midp{};
+  void prepare_mid() {
+    mid_first = mid_end = -1;
+    if (!(opt.fuse & 32) || opt.smoother != AMGB_SMOOTHER_JACOBI || opt.smoother_iters < 1 || L < 2 ||
+        !opt.skip_dead_coarse_smooth)
+      return;
+    const int end = (tail_first > 0) ? tail_first : L - 1;  // the level below the last mid level
+    const int64_t max_rows = env_int("AMGB_MID_ROWS", 70000);
+    auto eligible = [&](int l) {
+      if (l < 0 || l >= end) return false;
+      const LevelState& S = lv[l];
+      const DevMat& A = ops[l]->rows_of_A();
+      if (S.sharded || !S.tmp.p || !A.is_dia || A.dia.n_diag > mid::kMaxDiag || A.dia.rows.p || n[l] > max_rows) return false;
+      bool has_diag = false;
+      for (int d = 0; d < A.dia.n_diag; ++d) has_diag |= (A.dia.off[d] == 0);
+      return has_diag;
+    };
+    int first = end;
+    while (first - 1 >= 0 && end - (first - 1) <= mid::kMaxLevels && eligible(first - 1)) --first;
+    for (; first < end; ++first) {  // drop the finest candidate until a tile layout fits shared memory
+      mid::Params P{};
+      P.n_lv = end - first;
+      P.nu = (int)opt.smoother_iters;
+      P.first_is_level0 = (first == 0);
+      P.omega = opt.omega;
+      for (int l = first; l < end; ++l) {
+        mid::Level& V = P.lv[l - first];
+        const DevDia& D = ops[l]->rows_of_A().dia;
+        V.n = (int)n[l];
+        V.n_coarse = (int)n[l + 1];
+        V.nd = D.n_diag;
+        V.w = 0;
+        for (int d = 0; d < D.n_diag; ++d) {
+          V.off[d] = D.off[d];
+          if (D.off[d] == 0) V.diag_d = d;
+          V.w = std::max(V.w, std::abs(D.off[d]));
+        }
+        V.ld = D.ld;
+        V.val = D.val.p;
+        V.f = lv[l].f.p;
+        V.u = lv[l].u.p;
+        V.tmp = lv[l].tmp.p;
+      }
+      P.f_next = lv[end].f.p;
+      P.u_next = lv[end].u.p;
+      P.n_next = (int)n[end];
+      if (mid::plan_layout(P, 200 * 1024 / 8)) {
+        midp = P;
+        mid_first = first;
+        mid_end = end;
+        const int bytes = 8 * std::max(P.smem_doubles_down, P.smem_doubles_up);
+        if (bytes > 48 * 1024) {
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_down<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_down<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_up<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_up<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        }
+        return;
+      }
+    }
+  }
+  void mid_down(cudaStream_t s) {
+    const size_t bytes = 8 * (size_t)midp.smem_doubles_down;
+    if (fast_arith()) LAUNCH(mid::k_mid_down<true>, midp.n_blocks, 512, bytes, s, midp);
+    else LAUNCH(mid::k_mid_down<false>, midp.n_blocks, 512, bytes, s, midp);
+  }
+  void mid_up(cudaStream_t s) {
+    const size_t bytes = 8 * (size_t)midp.smem_doubles_up;
+    if (fast_arith()) LAUNCH(mid::k_mid_up<true>, midp.n_blocks, 512, bytes, s, midp);
+    else LAUNCH(mid::k_mid_up<false>, midp.n_blocks, 512, bytes, s, midp);
+  }
+
   void enqueue_vcycle(cudaStream_t s) {
     halo_exchanges_per_vcycle = 0;
     site_cursor = 0;  // sites 0 .. k-1 belong to the V-cycle, in the same order on every rank
     const int lt = (tail_first > 0) ? tail_first : L;  // levels [lt, L) run inside k_coarse_tail
-    for (int l = 0; l < lt; ++l) {
+    const int lm = (mid_first >= 0) ? mid_first : lt;  // levels [lm, mid_end) run inside the mid kernels
+    for (int l = 0; l < lm; ++l) {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
       if (leg_ok(l)) {  // sweeps + residual + restriction in one pass: u_l -> tmp_l, f_{l+1}
@@ -1335,9 +1416,11 @@ struct amgb_hierarchy {
       // on the coarsest level the reference also forms the residual (:272-274);
       // it is stored in a private member without a getter and never read.
     }
+    if (mid_first >= 0) mid_down(s);
     if (lt < L) LAUNCH(dev::k_coarse_tail, 1, 1024, tail_smem, s, tail);
     else coarse_solve(s);
-    for (int l = std::min(lt, L - 1) - 1; l >= 0; --l) {
+    if (mid_first >= 0) mid_up(s);
+    for (int l = std::min(lm, L - 1) - 1; l >= 0; --l) {
       if (leg_ok(l)) {  // tmp_l + P u_{l+1}, sweeps -> u_l
         if (lv[l].sharded) {
           if (leg_side[l]) CUDA_CHECK(cudaStreamWaitEvent(s, ev_leg[l], 0));
@@ -2181,6 +2264,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
   h->dwork.alloc(h->factor.n);
   CUDA_CHECK(cudaStreamSynchronize(s));
   h->prepare_tail();  // needs the factor on the device
+  h->prepare_mid();
   h->setup_p2p();
   *out = h.release();
 }
@@ -2622,6 +2706,14 @@ int amgb_coarse_solve(amgb_hierarchy* h) {
 }
 
 int amgb_hierarchy_tail_first(const amgb_hierarchy* h) { return h ? h->tail_first : -1; }
+int amgb_hierarchy_mid_range(const amgb_hierarchy* h, int* first, int* end, int* tile_rows, int* blocks) {
+  if (!h) return AMGB_EINVAL;
+  if (first) *first = h->mid_first;
+  if (end) *end = h->mid_end;
+  if (tile_rows) *tile_rows = h->mid_first >= 0 ? h->midp.T : 0;
+  if (blocks) *blocks = h->mid_first >= 0 ? h->midp.n_blocks : 0;
+  return AMGB_OK;
+}
 int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level) {
   return (h && h->leg_ok(level)) ? 1 : 0;
 }

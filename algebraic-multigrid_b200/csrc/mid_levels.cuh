@@ -1,0 +1,408 @@
+// Multi-level fused legs for the MID levels of the damped-Jacobi V-cycle (sm_100a).
+//
+// Below the levels that are worth streaming from HBM (stream_leg.cuh) and above the handful of
+// tiny levels that run in one block (k_coarse_tail), the levels of the hierarchy hold a few
+// thousand to a few ten thousand rows each: every kernel on them costs launch + dependency
+// latency, not bandwidth, and the per-operator path launches six of them per level.  Here ONE
+// kernel runs the down legs of ALL mid levels (multigrid.hpp:268-282 for each of them) and a
+// second one all their up legs (:294-301): a block owns a tile of rows of the first mid level
+// and the nested images of that tile on the deeper levels, keeps every level's vectors in shared
+// memory and recomputes a halo of rows around its tile so that it never needs a neighbouring
+// block's result (stage by stage the valid range shrinks by the level's half-bandwidth; the
+// coarser the level the fewer rows the halo costs).  Block barriers stand where the per-operator
+// path has launch boundaries; there is no grid-wide synchronisation.
+//
+// Per-row arithmetic is that of k_jacobi_zero / k_jacobi / k_residual / k_restrict /
+// k_prolong_add (kernels.cuh) in the same operation order -- bit-identical to them and to the
+// oracle in reference arithmetic; AMGB_ARITH_FAST uses FMAs and a refined reciprocal like the
+// streaming legs.
+//
+// The body is written against an `Env` (phase = run a lambda for every thread, barrier between
+// phases) so that tests/cpp/mid_levels_host.cpp runs the very same range logic serially on the
+// CPU and checks it against the oracle.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define AMGB_MID_FN __host__ __device__ __forceinline__
+#else
+#define AMGB_MID_FN inline
+#endif
+
+namespace amgb {
+namespace mid {
+
+constexpr int kMaxLevels = 8;
+constexpr int kMaxDiag = 16;
+
+struct Level {
+  int n;         // rows
+  int n_coarse;  // rows of the next level
+  int nd;        // diagonals, offsets ascending
+  int off[kMaxDiag];
+  int diag_d;    // index of the main diagonal
+  int w;         // half-bandwidth
+  int ld;
+  const double* val;  // rows of A in DIA: val[d * ld + row]
+  double* f;          // right-hand side (read on the first mid level, written on the deeper ones)
+  double* u;          // iterate at the end of the cycle
+  double* tmp;        // iterate after pre-smoothing (down kernel writes, up kernel reads)
+  // shared-memory layout (doubles): three buffers of `len` entries for the down kernel, three for the up kernel
+  int len_down, off_down;
+  int len_up, off_up;
+};
+
+struct Params {
+  int n_lv;             // mid levels
+  int nu;               // Jacobi sweeps per smooth call
+  int first_is_level0;  // the first mid level is the finest level: pre-smoothing starts from its u
+  int T;                // own rows per block on the first mid level (multiple of 2^n_lv)
+  int n_blocks;
+  double omega;
+  Level lv[kMaxLevels];
+  double* f_next;        // right-hand side of the level below the last mid level
+  const double* u_next;  // its solution (read by the up kernel)
+  int n_next;
+  int smem_doubles_down, smem_doubles_up;
+};
+
+struct Range {  // inclusive; empty when hi < lo
+  int lo, hi;
+};
+AMGB_MID_FN Range clip(Range r, int n) {
+  if (r.lo < 0) r.lo = 0;
+  if (r.hi > n - 1) r.hi = n - 1;
+  return r;
+}
+AMGB_MID_FN Range grow(Range r, int by, int n) { return clip(Range{r.lo - by, r.hi + by}, n); }
+AMGB_MID_FN Range hull(Range a, Range b) {
+  if (a.hi < a.lo) return b;
+  if (b.hi < b.lo) return a;
+  return Range{a.lo < b.lo ? a.lo : b.lo, a.hi > b.hi ? a.hi : b.hi};
+}
+AMGB_MID_FN bool inside(Range r, int k) { return k >= r.lo && k <= r.hi; }
+
+// stencil stages of a level's down leg, the residual included
+AMGB_MID_FN int down_stages(const Params& P, int i) { return (i == 0 && P.first_is_level0) ? P.nu + 1 : P.nu; }
+
+struct Plan {
+  Range own[kMaxLevels + 1];  // rows a block stores on each mid level (+ the level below)
+  Range res[kMaxLevels];      // down: rows whose residual is formed
+  Range in0[kMaxLevels];      // down: rows of the input stage (= rows whose f is needed)
+  Range fin[kMaxLevels];      // up: rows whose final iterate is needed (own rows + what the finer level interpolates from)
+  Range inp[kMaxLevels];      // up: rows of the input stage (tmp + P e)
+};
+
+AMGB_MID_FN void make_plan(const Params& P, int b, Plan& Q) {
+  // nested own ranges: coarse row J belongs to the owner of fine row 2J + 1
+  int lo = b * P.T, hi = lo + P.T;  // [lo, hi)
+  for (int i = 0; i <= P.n_lv; ++i) {
+    const int n = (i < P.n_lv) ? P.lv[i].n : P.n_next;
+    const bool last = (b == P.n_blocks - 1);
+    Q.own[i] = Range{lo < n ? lo : n, (last || hi > n ? n : hi) - 1};
+    lo >>= 1;
+    hi >>= 1;
+  }
+  // down pass, from the deepest level up: what the level below needs decides what this one computes
+  Range need_f = Q.own[P.n_lv];  // rows of the next level's f this block must produce
+  for (int i = P.n_lv - 1; i >= 0; --i) {
+    const Level& V = P.lv[i];
+    Range r = clip(Range{2 * need_f.lo, 2 * need_f.hi + 2}, V.n);
+    if (need_f.hi < need_f.lo) r = Range{0, -1};
+    r = hull(r, Q.own[i]);
+    Q.res[i] = r;
+    Q.in0[i] = (r.hi < r.lo) ? r : grow(r, down_stages(P, i) * V.w, V.n);
+    need_f = Q.in0[i];
+  }
+  // up pass, from the first level down: what the finer level interpolates from decides the final range
+  Range need_e{0, -1};
+  for (int i = 0; i < P.n_lv; ++i) {
+    const Level& V = P.lv[i];
+    Q.fin[i] = clip(hull(Q.own[i], need_e), V.n);
+    Q.inp[i] = (Q.fin[i].hi < Q.fin[i].lo) ? Q.fin[i] : grow(Q.fin[i], P.nu * V.w, V.n);
+    // fine row k reads coarse entries (k >> 1) - 1 (even k) and k >> 1
+    need_e = (Q.inp[i].hi < Q.inp[i].lo) ? Q.inp[i] : clip(Range{(Q.inp[i].lo >> 1) - 1, Q.inp[i].hi >> 1}, V.n_coarse);
+  }
+}
+
+// ---- arithmetic: reference order (bit-identical to kernels.cuh / the oracle) or fast ----
+template <bool FAST>
+struct Arith {
+  static AMGB_MID_FN double mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+  }
+  static AMGB_MID_FN double add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+  }
+  static AMGB_MID_FN double sub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+  }
+  static AMGB_MID_FN double div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+  }
+  static AMGB_MID_FN double rcp(double d) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = __fma_rn(-d, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-d, r, 1.0);
+    return __fma_rn(r, e, r);
+#else
+    return 1.0 / d;
+#endif
+  }
+  static AMGB_MID_FN double mulsub(double acc, double a, double x) {
+#if defined(__CUDA_ARCH__)
+    if (FAST) return __fma_rn(-a, x, acc);
+#endif
+    return sub(acc, mul(a, x));
+  }
+  static AMGB_MID_FN double relax(double x, double r, double d, double omega) {
+    if (d == 0.0) return x;
+    if (FAST) return x + (omega * rcp(d)) * r;
+    return add(x, mul(omega, div(r, d)));
+  }
+  static AMGB_MID_FN double relax_zero(double f, double d, double omega) {
+    if (d == 0.0) return 0.0;
+    if (FAST) return f * (omega * rcp(d));
+    return mul(omega, div(f, d));
+  }
+};
+
+AMGB_MID_FN double ld_global(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);  // vectors other kernels of the cycle wrote: L2, never the non-coherent path
+#else
+  return *p;
+#endif
+}
+AMGB_MID_FN double ld_const(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// f_k - sum_d a_d x[k + off_d], ascending column order; x is a shared-memory buffer whose entry 0 is row x_base
+template <bool FAST>
+AMGB_MID_FN double stencil(const Level& V, int k, double fk, const double* x, int x_base) {
+  double acc = fk;
+  for (int d = 0; d < V.nd; ++d) {
+    const double a = ld_const(V.val + (size_t)d * V.ld + k);
+    if (a != 0.0) acc = Arith<FAST>::mulsub(acc, a, x[k + V.off[d] - x_base]);
+  }
+  return acc;
+}
+
+// ---- the down legs of all mid levels for block b
+template <bool FAST, class Env>
+AMGB_MID_FN void run_down(const Params& P, int b, Env& env) {
+  Plan Q;
+  make_plan(P, b, Q);
+  double* sm = env.smem();
+  for (int i = 0; i < P.n_lv; ++i) {
+    const Level& V = P.lv[i];
+    const Range in0 = Q.in0[i], res = Q.res[i], own = Q.own[i];
+    if (in0.hi < in0.lo) continue;  // uniform over the block
+    double* A = sm + V.off_down;
+    double* B = A + V.len_down;
+    double* F = B + V.len_down;
+    const int base = in0.lo;
+    const bool from_u = (i == 0 && P.first_is_level0);
+    const int NS = down_stages(P, i);
+    // right-hand side of the first mid level comes from global memory, deeper ones were restricted into F
+    if (i == 0) {
+      env.phase([&](int t, int nt) {
+        for (int k = in0.lo + t; k <= in0.hi; k += nt) F[k - base] = ld_global(V.f + k);
+      });
+      env.sync();
+    }
+    // input stage: the stored iterate (finest level) or the first sweep from the zero guess
+    env.phase([&](int t, int nt) {
+      for (int k = in0.lo + t; k <= in0.hi; k += nt) {
+        double v;
+        if (from_u) v = ld_global(V.u + k);
+        else v = Arith<FAST>::relax_zero(F[k - base], ld_const(V.val + (size_t)V.diag_d * V.ld + k), P.omega);
+        A[k - base] = v;
+        if (NS == 1 && inside(own, k)) V.tmp[k] = v;  // one sweep: this already is the smoothed iterate
+      }
+    });
+    env.sync();
+    double* src = A;
+    double* dst = B;
+    for (int s = 1; s <= NS; ++s) {
+      const Range r = grow(res, (NS - s) * V.w, V.n);
+      env.phase([&](int t, int nt) {
+        for (int k = r.lo + t; k <= r.hi; k += nt) {
+          const double acc = stencil<FAST>(V, k, F[k - base], src, base);
+          if (s == NS) {
+            dst[k - base] = acc;  // residual
+          } else {
+            const double v = Arith<FAST>::relax(src[k - base], acc, ld_const(V.val + (size_t)V.diag_d * V.ld + k), P.omega);
+            dst[k - base] = v;
+            if (s == NS - 1 && inside(own, k)) V.tmp[k] = v;
+          }
+        }
+      });
+      env.sync();
+      double* t2 = src;
+      src = dst;
+      dst = t2;
+    }
+    // restriction of the residual (interpolator.hpp:64-68): into the next level's F and, for the rows
+    // this block owns, into that level's right-hand side in global memory
+    const bool deeper = (i + 1 < P.n_lv);
+    const Range cr = deeper ? Q.in0[i + 1] : Q.own[i + 1];
+    double* Fn = deeper ? sm + P.lv[i + 1].off_down + 2 * P.lv[i + 1].len_down : nullptr;
+    double* fg = deeper ? P.lv[i + 1].f : P.f_next;
+    const Range cown = Q.own[i + 1];
+    env.phase([&](int t, int nt) {
+      for (int J = cr.lo + t; J <= cr.hi; J += nt) {
+        double acc = 0.0;
+        const int k = 2 * J;
+        if (k < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, src[k - base]));
+        if (k + 1 < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(1.0, src[k + 1 - base]));
+        if (k + 2 < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, src[k + 2 - base]));
+        if (Fn) Fn[J - cr.lo] = acc;
+        if (inside(cown, J)) fg[J] = acc;
+      }
+    });
+    env.sync();
+  }
+}
+
+// ---- the up legs of all mid levels for block b
+template <bool FAST, class Env>
+AMGB_MID_FN void run_up(const Params& P, int b, Env& env) {
+  Plan Q;
+  make_plan(P, b, Q);
+  double* sm = env.smem();
+  const double* e = P.u_next;  // coarse correction of the level being processed: global at first, then shared
+  int e_base = 0;
+  bool e_global = true;
+  for (int i = P.n_lv - 1; i >= 0; --i) {
+    const Level& V = P.lv[i];
+    const Range inp = Q.inp[i], fin = Q.fin[i], own = Q.own[i];
+    if (inp.hi < inp.lo) continue;
+    double* A = sm + V.off_up;
+    double* B = A + V.len_up;
+    double* F = B + V.len_up;
+    const int base = inp.lo;
+    // input: tmp + P e (interpolator.hpp:52-56, multigrid.hpp:294-296), and the level's right-hand side
+    env.phase([&](int t, int nt) {
+      for (int k = inp.lo + t; k <= inp.hi; k += nt) {
+        double acc = 0.0;
+        const int J = k >> 1;
+        auto ev = [&](int j) { return e_global ? ld_global(e + j) : e[j - e_base]; };
+        if (k & 1) {
+          if (J < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(1.0, ev(J)));
+        } else {
+          if (J - 1 >= 0 && J - 1 < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, ev(J - 1)));
+          if (J < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, ev(J)));
+        }
+        A[k - base] = Arith<FAST>::add(ld_global(V.tmp + k), acc);
+        F[k - base] = ld_global(V.f + k);
+      }
+    });
+    env.sync();
+    double* src = A;
+    double* dst = B;
+    for (int s = 1; s <= P.nu; ++s) {
+      const Range r = grow(fin, (P.nu - s) * V.w, V.n);
+      env.phase([&](int t, int nt) {
+        for (int k = r.lo + t; k <= r.hi; k += nt) {
+          const double acc = stencil<FAST>(V, k, F[k - base], src, base);
+          const double v = Arith<FAST>::relax(src[k - base], acc, ld_const(V.val + (size_t)V.diag_d * V.ld + k), P.omega);
+          dst[k - base] = v;
+          if (s == P.nu && inside(own, k)) V.u[k] = v;
+        }
+      });
+      env.sync();
+      double* t2 = src;
+      src = dst;
+      dst = t2;
+    }
+    e = src;
+    e_base = base;
+    e_global = false;
+  }
+}
+
+// ---- shared-memory layout and tile size (host).  Returns false when no tile size fits `cap_doubles`.
+inline bool plan_layout(Params& P, int cap_doubles) {
+  const int gran = 1 << P.n_lv;
+  for (int T = 1024; T >= 64; T >>= 1) {
+    if (T % gran) continue;
+    P.T = T;
+    P.n_blocks = (P.lv[0].n + T - 1) / T;
+    int len_d[kMaxLevels] = {0}, len_u[kMaxLevels] = {0};
+    for (int b = 0; b < P.n_blocks; ++b) {
+      Plan Q;
+      make_plan(P, b, Q);
+      for (int i = 0; i < P.n_lv; ++i) {
+        const int ld = Q.in0[i].hi - Q.in0[i].lo + 1, lu = Q.inp[i].hi - Q.inp[i].lo + 1;
+        if (ld > len_d[i]) len_d[i] = ld;
+        if (lu > len_u[i]) len_u[i] = lu;
+      }
+    }
+    int od = 0, ou = 0;
+    for (int i = 0; i < P.n_lv; ++i) {
+      P.lv[i].len_down = (len_d[i] + 1) & ~1;
+      P.lv[i].off_down = od;
+      od += 3 * P.lv[i].len_down;
+      P.lv[i].len_up = (len_u[i] + 1) & ~1;
+      P.lv[i].off_up = ou;
+      ou += 3 * P.lv[i].len_up;
+    }
+    P.smem_doubles_down = od;
+    P.smem_doubles_up = ou;
+    if (od <= cap_doubles && ou <= cap_doubles) return true;
+  }
+  return false;
+}
+
+#if defined(__CUDACC__)
+struct DeviceEnv {
+  double* sm;
+  __device__ __forceinline__ double* smem() { return sm; }
+  template <class F>
+  __device__ __forceinline__ void phase(F&& f) {
+    f((int)threadIdx.x, (int)blockDim.x);
+  }
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+template <bool FAST>
+__global__ void __launch_bounds__(512) k_mid_down(const __grid_constant__ Params P) {
+  extern __shared__ __align__(16) double mid_smem[];
+  DeviceEnv env{mid_smem};
+  run_down<FAST>(P, (int)blockIdx.x, env);
+}
+template <bool FAST>
+__global__ void __launch_bounds__(512) k_mid_up(const __grid_constant__ Params P) {
+  extern __shared__ __align__(16) double mid_smem[];
+  DeviceEnv env{mid_smem};
+  run_up<FAST>(P, (int)blockIdx.x, env);
+}
+#endif
+
+}  // namespace mid
+}  // namespace amgb

@@ -155,8 +155,12 @@ typedef struct amgb_options {
                                operators that are 3 x 3 stencils over lines, one or two sweeps);
                                bit 3 (default off): TMA-ring fused legs for the other banded
                                levels; bit 4 (default on): the small coarse levels, the
-                               coarsest solve included, run in ONE kernel launch.  The
-                               arithmetic, hence every bit of the result, is unchanged   */
+                               coarsest solve included, run in ONE kernel launch; bit 5
+                               (default on): the mid levels between the streamed ones and
+                               that tail run all their down legs in one launch and all
+                               their up legs in another (shared-memory tiles with
+                               recomputed halos, mid_levels.cuh).  The arithmetic, hence
+                               every bit of the result, is unchanged                      */
   int arith;                /* arithmetic of the damped-Jacobi cycle's kernels.
                                AMGB_ARITH_REFERENCE (default): the oracle's operation order,
                                separate multiply / subtract, IEEE division -- bit-identical
@@ -298,6 +302,9 @@ int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level);
 /* first level of the coarse tail that runs in one launch (option fuse bit 4), -1 if none */
 int amgb_hierarchy_tail_first(const amgb_hierarchy* h);
 int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info);
+/* levels [first, end) that run inside the two mid-level kernels (option fuse bit 5; first = -1:
+ * none), rows of the first of them a block owns, and the number of blocks */
+int amgb_hierarchy_mid_range(const amgb_hierarchy* h, int* first, int* end, int* tile_rows, int* blocks);
 
 /* Device-side Galerkin product of one level (measured, not yet used by
  * the setup): A_{level+1} = R (A_level P) from the level's device mirror, one thread per coarse row,

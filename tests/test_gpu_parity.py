@@ -721,3 +721,27 @@ def test_mirror_cache_sees_in_place_edits():
     want = O.rss(A2o, u, b)
     got = amg.rss(A, u, b)
     assert abs(got - want) <= 1e-13 * want and abs(got - r0) > 1e-3 * r0
+
+
+# ----------------------------------------------------------------- mid levels (fuse bit 5, mid_levels.cuh)
+@pytest.mark.parametrize("n,L,eps,nu", [(35, 8, 1.0, 2), (64, 9, 1.0, 3), (100, 11, 1.0, 2), (129, 12, 1e-3, 2),
+                                        (257, 14, 1.0, 2), (513, 15, 1.0, 1)])
+@pytest.mark.parametrize("tail_rows,fuse", [("6000", 1 | 4 | 16 | 32), ("300", 1 | 4 | 16 | 32), ("6000", 32)])
+def test_mid_levels_are_bit_identical(monkeypatch, n, L, eps, nu, tail_rows, fuse):
+    """All down legs of the mid levels in one launch, all up legs in another (shared-memory tiles with
+    recomputed halos), alone and together with the streaming legs / the coarse tail: every level's
+    iterate and right-hand side bit-identical to the oracle."""
+    monkeypatch.setenv("AMGB_TAIL_ROWS", tail_rows)
+    sm = amg.DampedJacobi(2.0 / 3.0, nu)
+    mid, mo, _ = make_pair(n, L, sm, eps, fuse=fuse)
+    plain, _, _ = make_pair(n, L, sm, eps, fuse=0)
+    first, end, tile, blocks = mid.mid_range()
+    assert 0 <= first < end <= L - 1 and tile > 0 and blocks > 0
+    assert plain.mid_range()[0] == -1
+    for _ in range(3):
+        mid.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert mid.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert mid.get_rhs(l).tobytes() == mo.f(l).tobytes(), l
+    plain.vcycle()
+    assert mid.launches_per_vcycle() < plain.launches_per_vcycle()
