@@ -692,6 +692,10 @@ struct amgb_hierarchy {
   long long halo_timeout_cycles = 8000000000ll;  // ~4 s of clock64; AMGB_HALO_TIMEOUT_MS overrides
   int n_sites = 0, site_cursor = 0;
   static constexpr int kMaxSites = 4096;
+  static constexpr int kMaxLegSites = 64;  // fused legs: one site per sharded level and leg
+  DevBuf<unsigned long long> leg_epochs;   // [leg site][side]
+  DevBuf<unsigned int> leg_done;           // [leg site][side]
+  bool fused_push = false;                 // the legs push their boundary rows themselves (no exchange launches)
   // second stream: the halo exchange of a sweep runs beside the sweep of the block interior
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -737,8 +741,14 @@ struct amgb_hierarchy {
     const char* env = std::getenv("AMGB_HALO");
     if (env && std::string(env) == "nccl") return;
     const int G = world(), g = rank();
-    flags.alloc((size_t)kMaxSites * 4);  // [site][bumped by lower / upper neighbour][arrived, data]
+    // [site][bumped by lower / upper neighbour][arrived, data] of the stand-alone exchanges, then
+    // [leg site][bumped by lower / upper neighbour] of the fused legs (struct sleg::Sync)
+    flags.alloc((size_t)kMaxSites * 4 + (size_t)kMaxLegSites * 2);
     flags.zero(stream);
+    leg_epochs.alloc((size_t)kMaxLegSites * 2);
+    leg_epochs.zero(stream);
+    leg_done.alloc((size_t)kMaxLegSites * 2);
+    leg_done.zero(stream);
     epochs.alloc((size_t)kMaxSites * 2);
     epochs.zero(stream);
     CUDA_CHECK(cudaHostAlloc(&timed_out_host, sizeof(int), cudaHostAllocMapped));
@@ -800,6 +810,87 @@ struct amgb_hierarchy {
     // every rank must agree, otherwise some would wait for flags nobody bumps
     scalar_host_and(mapped);
     p2p = mapped;
+    const char* fp = std::getenv("AMGB_FUSED_PUSH");
+    if (p2p && !(fp && std::string(fp) == "0")) wire_leg_sync();
+  }
+  // Fused halo push (stream_leg_api.hpp, struct Sync): when every sharded level runs as streaming legs,
+  // each leg kernel is a site; its edge warps wait for the neighbours' previous site and push the rows
+  // the neighbours keep as ghost rows straight into their vectors.  No exchange launch remains on the
+  // sharded levels.
+  void wire_leg_sync() {
+    fused_push = false;
+    const int ns = n_sharded, G = world(), g = rank();
+    if (ns < 1 || 2 * ns > kMaxLegSites) return;
+    for (int l = 0; l < ns; ++l)
+      if (!leg_ok(l) || !legs[l].stream) return;
+    const int K = 2 * ns;
+    auto leg_flag = [&](unsigned long long* base, int site, int side) { return base + (size_t)kMaxSites * 4 + 2 * site + side; };
+    auto wire = [&](int l, bool up) {
+      sleg::Params& P = up ? legs[l].sup : legs[l].sdown;
+      const LevelState& S = lv[l];
+      const int site = up ? K - 1 - l : l, prev = (site + K - 1) % K;
+      const int NS = sleg::stages(up ? sleg::UP : legs[l].kind_down, P.nu);
+      sleg::Sync& Y = P.sync;
+      Y = sleg::Sync{};
+      Y.enabled = 1;
+      Y.timed_out = timed_out_dev;
+      Y.timeout_cycles = halo_timeout_cycles;
+      for (int side = 0; side < 2; ++side) {
+        const bool has = side == 0 ? g > 0 : g + 1 < G;
+        unsigned long long* peer_flags = side == 0 ? peer_flags_lo : peer_flags_hi;
+        Y.wait_flag[side] = has ? leg_flag(flags.p, prev, side) : nullptr;
+        Y.wait_epoch[side] = leg_epochs.p + 2 * prev + side;
+        Y.epoch[side] = leg_epochs.p + 2 * site + side;
+        Y.peer_flag[side] = has ? leg_flag(peer_flags, site, 1 - side) : nullptr;  // I am its neighbour on the other side
+        Y.done[side] = leg_done.p + 2 * site + side;
+      }
+      // output vector: the down leg writes tmp (vector 1), the up leg u (vector 0)
+      const int v = up ? 0 : 1;
+      const int n_lo = (g > 0) ? (int)(plan.start[l][g] - plan.start[l][g - 1]) : 0;  // rows of rank g-1's block
+      if (g > 0) {  // my first rows are rank g-1's upper ghost rows
+        Y.push_u[0].dst = peers[l].lo[v] + n_lo;
+        Y.push_u[0].begin = S.halo_lo;
+        Y.push_u[0].end = S.halo_lo + std::min(S.halo_hi, S.n_own);
+      }
+      if (g + 1 < G) {  // my last rows are rank g+1's lower ghost rows
+        Y.push_u[1].dst = peers[l].hi[v] - S.n_own;
+        Y.push_u[1].begin = S.halo_lo + S.n_own - std::min(S.halo_lo, S.n_own);
+        Y.push_u[1].end = S.halo_lo + S.n_own;
+      }
+      int lo_reach = P.own_begin, hi_reach = P.own_end;  // local fine rows whose producers / readers are edge warps
+      if (Y.push_u[0].dst) lo_reach = std::max(lo_reach, Y.push_u[0].end);
+      if (Y.push_u[1].dst) hi_reach = std::min(hi_reach, Y.push_u[1].begin);
+      if (!up && l + 1 < ns) {  // the coarse right-hand side goes into the neighbours' window of level l + 1
+        const LevelState& C = lv[l + 1];
+        const int c_lo = (g > 0) ? (int)(plan.start[l + 1][g] - plan.start[l + 1][g - 1]) : 0;
+        if (g > 0) {
+          Y.push_fc[0].dst = peers[l + 1].lo[2] + c_lo;
+          Y.push_fc[0].begin = C.halo_lo;
+          Y.push_fc[0].end = C.halo_lo + std::min(C.halo_hi, C.n_own);
+          lo_reach = std::max(lo_reach, 2 * (Y.push_fc[0].end + P.cbase) + 1 - P.base);
+        }
+        if (g + 1 < G) {
+          Y.push_fc[1].dst = peers[l + 1].hi[2] - C.n_own;
+          Y.push_fc[1].begin = C.halo_lo + C.n_own - std::min(C.halo_lo, C.n_own);
+          Y.push_fc[1].end = C.halo_lo + C.n_own;
+          hi_reach = std::min(hi_reach, 2 * (Y.push_fc[1].begin + P.cbase) - P.base);
+        }
+      }
+      // edge chunks: those that read ghost rows (within NS + 2 lines of the block edge) or produce pushed rows
+      const int64_t rows_per_chunk = (int64_t)P.LJ * P.m;
+      const int64_t lo_bound = (int64_t)lo_reach + (int64_t)(NS + 2) * P.m;
+      const int64_t hi_bound = (int64_t)hi_reach - (int64_t)(NS + 2) * P.m;
+      Y.edge_lo_chunks = (int)std::min<int64_t>(P.n_chunks, (lo_bound + rows_per_chunk - 1) / rows_per_chunk);
+      Y.edge_lo_chunks = std::max(Y.edge_lo_chunks, 1);
+      Y.edge_hi_chunk0 = hi_bound <= 0 ? 0 : (int)std::min<int64_t>(P.n_chunks - 1, hi_bound / rows_per_chunk);
+      Y.expected[0] = Y.edge_lo_chunks * P.n_strips;
+      Y.expected[1] = (P.n_chunks - Y.edge_hi_chunk0) * P.n_strips;
+    };
+    for (int l = 0; l < ns; ++l) {
+      wire(l, false);
+      wire(l, true);
+    }
+    fused_push = true;
   }
   // logical AND of a host bool over all ranks (NCCL all-reduce of one double)
   void scalar_host_and(bool& v) {
@@ -1389,7 +1480,12 @@ struct amgb_hierarchy {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
       if (leg_ok(l)) {  // sweeps + residual + restriction in one pass: u_l -> tmp_l, f_{l+1}
-        if (lv[l].sharded) {
+        if (lv[l].sharded && fused_push) {
+          // the leg waits for the neighbours' previous site itself and pushes its boundary rows
+          leg_down(l, s);
+          if (!lv[l + 1].sharded)  // first agglomerated level: every rank gets the whole right-hand side
+            allgather_blocks(lv[l + 1].f.p, coarse_block_start, s);
+        } else if (lv[l].sharded) {
           // ghost rows of the leg's input: the iterate on level 0, the right-hand side below
           exchange(l, l == 0 ? lv[l].u.p : lv[l].fw.p, s);
           leg_down(l, s);
@@ -1422,7 +1518,7 @@ struct amgb_hierarchy {
     if (mid_first >= 0) mid_up(s);
     for (int l = std::min(lm, L - 1) - 1; l >= 0; --l) {
       if (leg_ok(l)) {  // tmp_l + P u_{l+1}, sweeps -> u_l
-        if (lv[l].sharded) {
+        if (lv[l].sharded && !fused_push) {
           if (leg_side[l]) CUDA_CHECK(cudaStreamWaitEvent(s, ev_leg[l], 0));
           else exchange(l, lv[l].tmp.p, s);
           if (lv[l + 1].sharded) exchange(l + 1, lv[l + 1].u.p, s);
