@@ -1351,7 +1351,7 @@ struct amgb_hierarchy {
     const int bw = factor.bw, nc = factor.n;
     const size_t smem = sizeof(double) * (size_t)nc * (std::max(bw, 1) + 1);
     if (bw < 1 || bw > 8 || smem > 200 * 1024) return;
-    const int64_t max_rows = env_int("AMGB_TAIL_ROWS", 6000);
+    const int64_t max_rows = env_int("AMGB_TAIL_ROWS", (opt.fuse & 32) ? 1100 : 6000);  // with the mid kernels on, only the smallest levels
     int first = L - 1;  // the coarsest level alone is just the solve
     while (first - 1 >= 1 && first - 1 >= L - 1 - dev::kTailMaxLevels && n[first - 1] <= max_rows) {
       const int l = first - 1;
@@ -1451,10 +1451,10 @@ struct amgb_hierarchy {
         mid_end = end;
         const int bytes = 8 * std::max(P.smem_doubles_down, P.smem_doubles_up);
         if (bytes > 48 * 1024) {
-          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_down<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_down<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_up<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid_up<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+          CUDA_CHECK(cudaFuncSetAttribute(mid::k_mid<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         }
         return;
       }
@@ -1462,13 +1462,15 @@ struct amgb_hierarchy {
   }
   void mid_down(cudaStream_t s) {
     const size_t bytes = 8 * (size_t)midp.smem_doubles_down;
-    if (fast_arith()) LAUNCH(mid::k_mid_down<true>, midp.n_blocks, 512, bytes, s, midp);
-    else LAUNCH(mid::k_mid_down<false>, midp.n_blocks, 512, bytes, s, midp);
+    const int threads = env_int("AMGB_MID_THREADS", 1024);
+    if (fast_arith()) LAUNCH((mid::k_mid<true, false>), midp.n_blocks, threads, bytes, s, midp);
+    else LAUNCH((mid::k_mid<false, false>), midp.n_blocks, threads, bytes, s, midp);
   }
   void mid_up(cudaStream_t s) {
     const size_t bytes = 8 * (size_t)midp.smem_doubles_up;
-    if (fast_arith()) LAUNCH(mid::k_mid_up<true>, midp.n_blocks, 512, bytes, s, midp);
-    else LAUNCH(mid::k_mid_up<false>, midp.n_blocks, 512, bytes, s, midp);
+    const int threads = env_int("AMGB_MID_THREADS", 1024);
+    if (fast_arith()) LAUNCH((mid::k_mid<true, true>), midp.n_blocks, threads, bytes, s, midp);
+    else LAUNCH((mid::k_mid<false, true>), midp.n_blocks, threads, bytes, s, midp);
   }
 
   void enqueue_vcycle(cudaStream_t s) {
@@ -2960,6 +2962,34 @@ int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level) {
 int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int reps, double* ms_out) {
   return guarded([&] {
     if (!h || !ms_out || reps < 1) throw std::invalid_argument("bad argument");
+    if (kind >= 6 && kind <= 8) {
+      // 6 / 7: the mid-level down / up kernel, 8: the coarse tail (or the coarsest solve alone).  They are
+      // timed on the live level state (a cycle's worth of it): nothing to restore, every run computes
+      // the same values from the same inputs.
+      CUDA_CHECK(cudaSetDevice(h->device));
+      cudaStream_t s = h->stream;
+      if ((kind == 6 || kind == 7) && h->mid_first < 0) throw ApiError(AMGB_ESTATE, "no mid levels");
+      auto once = [&] {
+        if (kind == 6) h->mid_down(s);
+        else if (kind == 7) h->mid_up(s);
+        else if (h->tail_first > 0) LAUNCH(dev::k_coarse_tail, 1, 1024, h->tail_smem, s, h->tail);
+        else h->coarse_solve(s);
+      };
+      for (int i = 0; i < warmup; ++i) once();
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, s));
+      for (int i = 0; i < reps; ++i) once();
+      CUDA_CHECK(cudaEventRecord(e1, s));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      *ms_out = (double)ms / reps;
+      return;
+    }
     h->check_level(level, kind >= 2);
     if (kind == 2 || kind == 3) h->require_whole(level);
     if (kind == 4 || kind == 5) {

@@ -64,6 +64,9 @@ struct Params {
   double* f_next;        // right-hand side of the level below the last mid level
   const double* u_next;  // its solution (read by the up kernel)
   int n_next;
+  // shared memory (doubles): per-level vector buffers first, then ONE coefficient buffer (the DIA
+  // rows of the level being processed, val[d * len + j]) that every level reuses
+  int coef_off_down, coef_off_up;
   int smem_doubles_down, smem_doubles_up;
 };
 
@@ -202,13 +205,27 @@ AMGB_MID_FN double ld_const(const double* p) {
 #endif
 }
 
-// f_k - sum_d a_d x[k + off_d], ascending column order; x is a shared-memory buffer whose entry 0 is row x_base
+// The level's operator rows [base, base + cnt) into shared memory, Cf[d * len + j] = A(base + j, diagonal d),
+// plus up to two vectors over the same rows: ONE round of bulk copies (TMA, cp.async.bulk + mbarrier on
+// the device; memcpy in the host Env) instead of a latency chain per entry.  base is even and cnt a
+// multiple of two, so every copy is 16-byte aligned (the DIA rows and the level vectors are padded).
+template <class Env>
+AMGB_MID_FN void load_level(const Level& V, int base, int cnt, int len, double* Cf, double* v0, const double* g0,
+                            double* v1, const double* g1, Env& env) {
+  env.bulk_start((V.nd + (g0 ? 1 : 0) + (g1 ? 1 : 0)) * cnt);
+  for (int d = 0; d < V.nd; ++d) env.bulk_copy(Cf + (size_t)d * len, V.val + (size_t)d * V.ld + base, cnt);
+  if (g0) env.bulk_copy(v0, g0 + base, cnt);
+  if (g1) env.bulk_copy(v1, g1 + base, cnt);
+  env.bulk_wait();
+}
+// f_k - sum_d a_d x[k + off_d], ascending column order; Cf and x are shared-memory buffers whose entry 0 is row `base`
 template <bool FAST>
-AMGB_MID_FN double stencil(const Level& V, int k, double fk, const double* x, int x_base) {
+AMGB_MID_FN double stencil(const Level& V, int k, double fk, const double* Cf, int len, const double* x, int base) {
   double acc = fk;
+  const int j = k - base;
   for (int d = 0; d < V.nd; ++d) {
-    const double a = ld_const(V.val + (size_t)d * V.ld + k);
-    if (a != 0.0) acc = Arith<FAST>::mulsub(acc, a, x[k + V.off[d] - x_base]);
+    const double a = Cf[(size_t)d * len + j];
+    if (a != 0.0) acc = Arith<FAST>::mulsub(acc, a, x[j + V.off[d]]);
   }
   return acc;
 }
@@ -226,22 +243,23 @@ AMGB_MID_FN void run_down(const Params& P, int b, Env& env) {
     double* A = sm + V.off_down;
     double* B = A + V.len_down;
     double* F = B + V.len_down;
-    const int base = in0.lo;
+    double* Cf = sm + P.coef_off_down;
+    const int len = V.len_down;
+    const int base = in0.lo & ~1;
+    const int cnt = (in0.hi - base + 2) & ~1;
     const bool from_u = (i == 0 && P.first_is_level0);
     const int NS = down_stages(P, i);
-    // right-hand side of the first mid level comes from global memory, deeper ones were restricted into F
-    if (i == 0) {
-      env.phase([&](int t, int nt) {
-        for (int k = in0.lo + t; k <= in0.hi; k += nt) F[k - base] = ld_global(V.f + k);
-      });
-      env.sync();
-    }
+    // operator rows of this block's range into shared memory; the right-hand side of the first mid level
+    // (and the stored iterate of the finest level) come from global memory, deeper right-hand sides were
+    // restricted into F by the level above
+    load_level(V, base, cnt, len, Cf, i == 0 ? F : nullptr, i == 0 ? V.f : nullptr, from_u ? A : nullptr,
+               from_u ? V.u : nullptr, env);
     // input stage: the stored iterate (finest level) or the first sweep from the zero guess
     env.phase([&](int t, int nt) {
       for (int k = in0.lo + t; k <= in0.hi; k += nt) {
         double v;
-        if (from_u) v = ld_global(V.u + k);
-        else v = Arith<FAST>::relax_zero(F[k - base], ld_const(V.val + (size_t)V.diag_d * V.ld + k), P.omega);
+        if (from_u) v = A[k - base];
+        else v = Arith<FAST>::relax_zero(F[k - base], Cf[(size_t)V.diag_d * len + (k - base)], P.omega);
         A[k - base] = v;
         if (NS == 1 && inside(own, k)) V.tmp[k] = v;  // one sweep: this already is the smoothed iterate
       }
@@ -253,11 +271,11 @@ AMGB_MID_FN void run_down(const Params& P, int b, Env& env) {
       const Range r = grow(res, (NS - s) * V.w, V.n);
       env.phase([&](int t, int nt) {
         for (int k = r.lo + t; k <= r.hi; k += nt) {
-          const double acc = stencil<FAST>(V, k, F[k - base], src, base);
+          const double acc = stencil<FAST>(V, k, F[k - base], Cf, len, src, base);
           if (s == NS) {
             dst[k - base] = acc;  // residual
           } else {
-            const double v = Arith<FAST>::relax(src[k - base], acc, ld_const(V.val + (size_t)V.diag_d * V.ld + k), P.omega);
+            const double v = Arith<FAST>::relax(src[k - base], acc, Cf[(size_t)V.diag_d * len + (k - base)], P.omega);
             dst[k - base] = v;
             if (s == NS - 1 && inside(own, k)) V.tmp[k] = v;
           }
@@ -282,7 +300,7 @@ AMGB_MID_FN void run_down(const Params& P, int b, Env& env) {
         if (k < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, src[k - base]));
         if (k + 1 < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(1.0, src[k + 1 - base]));
         if (k + 2 < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, src[k + 2 - base]));
-        if (Fn) Fn[J - cr.lo] = acc;
+        if (Fn) Fn[J - (cr.lo & ~1)] = acc;
         if (inside(cown, J)) fg[J] = acc;
       }
     });
@@ -306,8 +324,13 @@ AMGB_MID_FN void run_up(const Params& P, int b, Env& env) {
     double* A = sm + V.off_up;
     double* B = A + V.len_up;
     double* F = B + V.len_up;
-    const int base = inp.lo;
-    // input: tmp + P e (interpolator.hpp:52-56, multigrid.hpp:294-296), and the level's right-hand side
+    double* Cf = sm + P.coef_off_up;
+    const int len = V.len_up;
+    const int base = inp.lo & ~1;
+    const int cnt = (inp.hi - base + 2) & ~1;
+    // operator rows, pre-smoothed iterate and right-hand side of this block's range into shared memory
+    load_level(V, base, cnt, len, Cf, A, V.tmp, F, V.f, env);
+    // input: tmp + P e (interpolator.hpp:52-56, multigrid.hpp:294-296)
     env.phase([&](int t, int nt) {
       for (int k = inp.lo + t; k <= inp.hi; k += nt) {
         double acc = 0.0;
@@ -319,8 +342,7 @@ AMGB_MID_FN void run_up(const Params& P, int b, Env& env) {
           if (J - 1 >= 0 && J - 1 < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, ev(J - 1)));
           if (J < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, ev(J)));
         }
-        A[k - base] = Arith<FAST>::add(ld_global(V.tmp + k), acc);
-        F[k - base] = ld_global(V.f + k);
+        A[k - base] = Arith<FAST>::add(A[k - base], acc);
       }
     });
     env.sync();
@@ -330,8 +352,8 @@ AMGB_MID_FN void run_up(const Params& P, int b, Env& env) {
       const Range r = grow(fin, (P.nu - s) * V.w, V.n);
       env.phase([&](int t, int nt) {
         for (int k = r.lo + t; k <= r.hi; k += nt) {
-          const double acc = stencil<FAST>(V, k, F[k - base], src, base);
-          const double v = Arith<FAST>::relax(src[k - base], acc, ld_const(V.val + (size_t)V.diag_d * V.ld + k), P.omega);
+          const double acc = stencil<FAST>(V, k, F[k - base], Cf, len, src, base);
+          const double v = Arith<FAST>::relax(src[k - base], acc, Cf[(size_t)V.diag_d * len + (k - base)], P.omega);
           dst[k - base] = v;
           if (s == P.nu && inside(own, k)) V.u[k] = v;
         }
@@ -348,9 +370,9 @@ AMGB_MID_FN void run_up(const Params& P, int b, Env& env) {
 }
 
 // ---- shared-memory layout and tile size (host).  Returns false when no tile size fits `cap_doubles`.
-inline bool plan_layout(Params& P, int cap_doubles) {
+inline bool plan_layout(Params& P, int cap_doubles, int force_T = 0) {
   const int gran = 1 << P.n_lv;
-  for (int T = 1024; T >= 64; T >>= 1) {
+  for (int T = force_T > 0 ? force_T : 1024; T >= (force_T > 0 ? force_T : 64); T >>= 1) {
     if (T % gran) continue;
     P.T = T;
     P.n_blocks = (P.lv[0].n + T - 1) / T;
@@ -366,41 +388,66 @@ inline bool plan_layout(Params& P, int cap_doubles) {
     }
     int od = 0, ou = 0;
     for (int i = 0; i < P.n_lv; ++i) {
-      P.lv[i].len_down = (len_d[i] + 1) & ~1;
+      P.lv[i].len_down = (len_d[i] + 3) & ~1;  // base is rounded down to even, the count up
       P.lv[i].off_down = od;
       od += 3 * P.lv[i].len_down;
-      P.lv[i].len_up = (len_u[i] + 1) & ~1;
+      P.lv[i].len_up = (len_u[i] + 3) & ~1;
       P.lv[i].off_up = ou;
       ou += 3 * P.lv[i].len_up;
     }
-    P.smem_doubles_down = od;
-    P.smem_doubles_up = ou;
-    if (od <= cap_doubles && ou <= cap_doubles) return true;
+    int cd = 0, cu = 0;  // one coefficient buffer, sized for the level that needs the most
+    for (int i = 0; i < P.n_lv; ++i) {
+      if (P.lv[i].nd * P.lv[i].len_down > cd) cd = P.lv[i].nd * P.lv[i].len_down;
+      if (P.lv[i].nd * P.lv[i].len_up > cu) cu = P.lv[i].nd * P.lv[i].len_up;
+    }
+    P.coef_off_down = od;
+    P.coef_off_up = ou;
+    P.smem_doubles_down = od + cd;
+    P.smem_doubles_up = ou + cu;
+    if (P.smem_doubles_down <= cap_doubles && P.smem_doubles_up <= cap_doubles) return true;
   }
   return false;
 }
 
 #if defined(__CUDACC__)
+// thread 0 issues the bulk copies of a round; every thread waits on the block's mbarrier
 struct DeviceEnv {
   double* sm;
+  uint64_t* bar;
+  uint32_t parity;
   __device__ __forceinline__ double* smem() { return sm; }
   template <class F>
   __device__ __forceinline__ void phase(F&& f) {
     f((int)threadIdx.x, (int)blockDim.x);
   }
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void bulk_start(int doubles) {
+    if (threadIdx.x == 0) {
+      // the buffers were last read before the block barrier that ended the previous phase
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      dev::mbar_expect_tx(bar, (uint32_t)doubles * 8u);
+    }
+  }
+  __device__ __forceinline__ void bulk_copy(double* dst, const double* src, int doubles) {
+    if (threadIdx.x == 0) dev::tma_load_1d(dst, src, (uint32_t)doubles * 8u, bar);
+  }
+  __device__ __forceinline__ void bulk_wait() {
+    dev::mbar_wait(bar, parity);
+    parity ^= 1u;
+  }
 };
-template <bool FAST>
-__global__ void __launch_bounds__(512) k_mid_down(const __grid_constant__ Params P) {
+template <bool FAST, bool UP>
+__global__ void __launch_bounds__(1024) k_mid(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) double mid_smem[];
-  DeviceEnv env{mid_smem};
-  run_down<FAST>(P, (int)blockIdx.x, env);
-}
-template <bool FAST>
-__global__ void __launch_bounds__(512) k_mid_up(const __grid_constant__ Params P) {
-  extern __shared__ __align__(16) double mid_smem[];
-  DeviceEnv env{mid_smem};
-  run_up<FAST>(P, (int)blockIdx.x, env);
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    dev::mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  DeviceEnv env{mid_smem, &bar, 0u};
+  if (UP) run_up<FAST>(P, (int)blockIdx.x, env);
+  else run_down<FAST>(P, (int)blockIdx.x, env);
 }
 #endif
 

@@ -331,7 +331,8 @@ int64_t amgb_hierarchy_vcycle_bytes(const amgb_hierarchy* h);
  * Per-kernel timing hooks for bench.py (CUDA events on the handle's stream).
  * kind: 0 smoother pass (one Jacobi sweep / one colour-complete pass / one GS
  * direction), 1 residual, 2 residual+restrict, 3 prolong+add, 4 fused down leg,
- * 5 fused up leg (levels with amgb_hierarchy_fused_legs).  Runs `reps`
+ * 5 fused up leg (levels with amgb_hierarchy_fused_legs), 6 / 7 the mid-level down / up
+ * kernel, 8 the coarse tail (level ignored for 6-8).  Runs `reps`
  * launches after `warmup`, returns the mean milliseconds per launch.
  * ---------------------------------------------------------------------- */
 int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int reps,

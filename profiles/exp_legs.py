@@ -43,6 +43,10 @@ for setting in settings:
     for l in range(L - 1):
         if mg.fused_legs(l):
             legs.append("L%d %.1f/%.1f" % (l, mg.time_kernel(l, 4, 3, 20) * 1e3, mg.time_kernel(l, 5, 3, 20) * 1e3))
+    extra = ""
+    if mg.mid_range()[0] >= 0:
+        extra = "  mid %s down %.1f up %.1f" % (mg.mid_range(), mg.time_kernel(0, 6, 3, 20) * 1e3, mg.time_kernel(0, 7, 3, 20) * 1e3)
+    extra += "  tail %.1f" % (mg.time_kernel(0, 8, 3, 20) * 1e3)
     print("[%s] setup %.2f s  vcycle %.4f ms  launches %d  tail_first %d  legs(us down/up): %s" % (
-        setting, setup, cyc, mg.launches_per_vcycle(), mg.tail_first(), "  ".join(legs)), flush=True)
+        setting, setup, cyc, mg.launches_per_vcycle(), mg.tail_first(), "  ".join(legs) + extra), flush=True)
     del mg

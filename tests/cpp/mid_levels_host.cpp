@@ -22,6 +22,14 @@ struct HostEnv {
     for (int t = 0; t < nthreads; ++t) f(t, nthreads);
   }
   void sync() {}
+  // bulk copies land when they are issued; alignment rules of the device TMA path are checked
+  int bad = 0;
+  void bulk_start(int) {}
+  void bulk_copy(double* dst, const double* src, int doubles) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || ((dst - sm.data()) & 1) || (doubles & 1) || doubles <= 0) ++bad;
+    std::memcpy(dst, src, sizeof(double) * (size_t)doubles);
+  }
+  void bulk_wait() {}
 };
 }  // namespace
 
@@ -61,38 +69,10 @@ int mid_host_run(int n_lv, int nu, int first_is_level0, double omega, const int*
   P.f_next = f_next;
   P.u_next = u_next;
   P.n_next = n_next;
-  if (!plan_layout(P, cap_doubles)) return -1;
-  if (force_T > 0) {  // exercise small tiles: recompute the layout for this tile size only
-    Params Q = P;
-    bool ok = false;
-    for (int cap = cap_doubles; !ok && cap < (1 << 28); cap <<= 1) {
-      Q = P;
-      // plan_layout walks T downwards from 1024; emulate a fixed T by shrinking the first level's view
-      Q.T = force_T;
-      Q.n_blocks = (Q.lv[0].n + force_T - 1) / force_T;
-      int len_d[kMaxLevels] = {0}, len_u[kMaxLevels] = {0};
-      for (int b = 0; b < Q.n_blocks; ++b) {
-        Plan pl;
-        make_plan(Q, b, pl);
-        for (int i = 0; i < n_lv; ++i) {
-          len_d[i] = std::max(len_d[i], pl.in0[i].hi - pl.in0[i].lo + 1);
-          len_u[i] = std::max(len_u[i], pl.inp[i].hi - pl.inp[i].lo + 1);
-        }
-      }
-      int od = 0, ou = 0;
-      for (int i = 0; i < n_lv; ++i) {
-        Q.lv[i].len_down = (len_d[i] + 1) & ~1;
-        Q.lv[i].off_down = od;
-        od += 3 * Q.lv[i].len_down;
-        Q.lv[i].len_up = (len_u[i] + 1) & ~1;
-        Q.lv[i].off_up = ou;
-        ou += 3 * Q.lv[i].len_up;
-      }
-      Q.smem_doubles_down = od;
-      Q.smem_doubles_up = ou;
-      ok = true;
-    }
-    P = Q;
+  if (force_T > 0) {  // exercise small tiles (no shared-memory cap on the host)
+    if (!plan_layout(P, 1 << 28, force_T)) return -1;
+  } else if (!plan_layout(P, cap_doubles)) {
+    return -1;
   }
   if (tile) *tile = P.T;
   if (blocks) *blocks = P.n_blocks;
@@ -100,6 +80,7 @@ int mid_host_run(int n_lv, int nu, int first_is_level0, double omega, const int*
   const int words = std::max(P.smem_doubles_down, P.smem_doubles_up) + 2;
   for (int b = 0; b < P.n_blocks; ++b) {
     env.sm.assign(words, std::numeric_limits<double>::quiet_NaN());  // stale reads show up as NaN
+    if (reinterpret_cast<uintptr_t>(env.sm.data()) & 15) return -3;
     if (do_up) {
       if (fast) run_up<true>(P, b, env);
       else run_up<false>(P, b, env);
@@ -108,6 +89,6 @@ int mid_host_run(int n_lv, int nu, int first_is_level0, double omega, const int*
       else run_down<false>(P, b, env);
     }
   }
-  return 0;
+  return env.bad ? -4 : 0;
 }
 }

@@ -95,7 +95,7 @@ def test_mid_levels_down_and_up_bit_exact(n, L, first, n_lv, nu, eps, force_T):
     f_next = np.full(n_next, np.nan)
     tile, blocks = C.c_int(0), C.c_int(0)
     rc = Lh.mid_host_run(n_lv, nu, int(first == 0), OMEGA, nn, nd, off, ld, ptrs(val), ptrs(f), ptrs(u), ptrs(tmp),
-                         f_next, np.zeros(n_next), n_next, 0, 0, 25000, force_T, C.byref(tile), C.byref(blocks))
+                         f_next, np.zeros(n_next), n_next, 0, 0, 400000, force_T, C.byref(tile), C.byref(blocks))
     assert rc == 0
     if force_T:
         assert blocks.value > 1
@@ -114,7 +114,7 @@ def test_mid_levels_down_and_up_bit_exact(n, L, first, n_lv, nu, eps, force_T):
         mo.smooth(l)
         want_u[l] = mo.u(l).copy()
     rc = Lh.mid_host_run(n_lv, nu, int(first == 0), OMEGA, nn, nd, off, ld, ptrs(val), ptrs(f), ptrs(u), ptrs(tmp),
-                         f_next, u_next, n_next, 0, 1, 25000, force_T, C.byref(tile), C.byref(blocks))
+                         f_next, u_next, n_next, 0, 1, 400000, force_T, C.byref(tile), C.byref(blocks))
     assert rc == 0
     for i, l in enumerate(lv):
         assert u[i].tobytes() == want_u[l].tobytes(), ("u", l)
