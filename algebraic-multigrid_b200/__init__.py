@@ -121,6 +121,7 @@ SIGNATURES = {
     "amgb_residual_level": (_i, [_p, _i, _pd]),
     "amgb_residual_restrict_level": (_i, [_p, _i]),
     "amgb_coarse_solve": (_i, [_p]),
+    "amgb_hierarchy_phase_times": (_i, [_p, _i, _pd]),
     "amgb_kernel_launches": (_l, []),
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
     "amgb_hierarchy_fused_legs": (_i, [_p, _i]),
@@ -686,6 +687,12 @@ class Multigrid:
         ms, bad = _d(), _l()
         _check(lib().amgb_hierarchy_galerkin_device(self.h, level, C.byref(ms), C.byref(bad)))
         return ms.value, bad.value
+
+    def phase_times(self, reps=10):
+        """ms of [sharded down legs, gather, levels below the sharded ones, sharded up legs] on this rank."""
+        out = np.zeros(4)
+        _check(lib().amgb_hierarchy_phase_times(self.h, reps, out))
+        return dict(zip(("sharded_down", "gather", "coarse_part", "sharded_up"), out.tolist()))
 
     def tail_first(self):
         """First level of the coarse tail that runs in one launch (-1: none)."""

@@ -832,7 +832,7 @@ struct amgb_hierarchy {
       const int NS = sleg::stages(up ? sleg::UP : legs[l].kind_down, P.nu);
       sleg::Sync& Y = P.sync;
       Y = sleg::Sync{};
-      Y.enabled = 1;
+      Y.enabled = 1 | env_int("AMGB_SYNC_DEBUG", 0);  // bits 1-3 switch off wait / push / signal (timing experiments only)
       Y.timed_out = timed_out_dev;
       Y.timeout_cycles = halo_timeout_cycles;
       for (int side = 0; side < 2; ++side) {
@@ -1209,7 +1209,7 @@ struct amgb_hierarchy {
         P.n_lines = (P.n + P.m - 1) / P.m;
         P.Wu = 32 - 2 * (NS + X);
         P.n_strips = (P.m + P.Wu - 1) / P.Wu;
-        const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / 8));
+        const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / env_int("AMGB_SLEG_MINLINES", 8)));
         P.LJ = (P.n_lines + chunks - 1) / chunks;
         P.n_chunks = (P.n_lines + P.LJ - 1) / P.LJ;
         P.n_warps = P.n_strips * P.n_chunks;
@@ -1267,7 +1267,7 @@ struct amgb_hierarchy {
             P.n_lines = st.P.n_lines;
             P.Wu = 32 - 2 * (NS + X);
             P.n_strips = (P.m + P.Wu - 1) / P.Wu;
-            const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / 8));
+            const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / env_int("AMGB_SLEG_MINLINES", 8)));
             P.LJ = (P.n_lines + chunks - 1) / chunks;
             P.n_chunks = (P.n_lines + P.LJ - 1) / P.LJ;
             P.n_warps = P.n_strips * P.n_chunks;
@@ -1473,11 +1473,23 @@ struct amgb_hierarchy {
     else LAUNCH((mid::k_mid<false, true>), midp.n_blocks, threads, bytes, s, midp);
   }
 
+  // optional phase marks (amgb_hierarchy_phase_times): events recorded at the phase boundaries of an
+  // un-captured cycle -- [0] start, [1] sharded down legs done, [2] gather done, [3] replicated /
+  // single-GPU coarse part done (levels below the sharded ones, both directions), [4] end
+  cudaEvent_t* phase_ev = nullptr;
+  void mark(int i, cudaStream_t s) {
+    if (phase_ev) CUDA_CHECK(cudaEventRecord(phase_ev[i], s));
+  }
   void enqueue_vcycle(cudaStream_t s) {
     halo_exchanges_per_vcycle = 0;
     site_cursor = 0;  // sites 0 .. k-1 belong to the V-cycle, in the same order on every rank
     const int lt = (tail_first > 0) ? tail_first : L;  // levels [lt, L) run inside k_coarse_tail
     const int lm = (mid_first >= 0) ? mid_first : lt;  // levels [lm, mid_end) run inside the mid kernels
+    mark(0, s);
+    if (n_sharded == 0) {
+      mark(1, s);
+      mark(2, s);
+    }
     for (int l = 0; l < lm; ++l) {
       const bool coarsest = (l + 1 == L);
       if (coarsest && opt.skip_dead_coarse_smooth) break;
@@ -1485,8 +1497,11 @@ struct amgb_hierarchy {
         if (lv[l].sharded && fused_push) {
           // the leg waits for the neighbours' previous site itself and pushes its boundary rows
           leg_down(l, s);
-          if (!lv[l + 1].sharded)  // first agglomerated level: every rank gets the whole right-hand side
+          if (!lv[l + 1].sharded) {  // first agglomerated level: every rank gets the whole right-hand side
+            mark(1, s);
             allgather_blocks(lv[l + 1].f.p, coarse_block_start, s);
+            mark(2, s);
+          }
         } else if (lv[l].sharded) {
           // ghost rows of the leg's input: the iterate on level 0, the right-hand side below
           exchange(l, l == 0 ? lv[l].u.p : lv[l].fw.p, s);
@@ -1500,8 +1515,11 @@ struct amgb_hierarchy {
             exchange(l, lv[l].tmp.p, aux_stream);
             CUDA_CHECK(cudaEventRecord(ev_leg[l], aux_stream));
           }
-          if (!lv[l + 1].sharded)  // first agglomerated level: every rank gets the whole right-hand side
+          if (!lv[l + 1].sharded) {  // first agglomerated level: every rank gets the whole right-hand side
+            mark(1, s);
             allgather_blocks(lv[l + 1].f.p, coarse_block_start, s);
+            mark(2, s);
+          }
         } else {
           leg_down(l, s);
         }
@@ -1518,7 +1536,9 @@ struct amgb_hierarchy {
     if (lt < L) LAUNCH(dev::k_coarse_tail, 1, 1024, tail_smem, s, tail);
     else coarse_solve(s);
     if (mid_first >= 0) mid_up(s);
+    if (n_sharded == 0) mark(3, s);
     for (int l = std::min(lm, L - 1) - 1; l >= 0; --l) {
+      if (l == n_sharded - 1) mark(3, s);
       if (leg_ok(l)) {  // tmp_l + P u_{l+1}, sweeps -> u_l
         if (lv[l].sharded && !fused_push) {
           if (leg_side[l]) CUDA_CHECK(cudaStreamWaitEvent(s, ev_leg[l], 0));
@@ -1530,6 +1550,7 @@ struct amgb_hierarchy {
         smooth(l, s, false, /*with_prolong=*/true);
       }
     }
+    mark(4, s);
   }
   void build_graph() {
     if (exec) return;
@@ -2924,6 +2945,39 @@ int amgb_hierarchy_galerkin_device(amgb_hierarchy* h, int level, double* ms_out,
       if (!matched[c])
         for (int i = 0; i < n_c; ++i) bad += (got[(size_t)c * ld_c + i] != 0.0);
     if (mismatches) *mismatches = bad;
+  });
+}
+
+// Mean milliseconds of the four phases of a V-cycle on this rank over `reps` un-captured cycles:
+// out[0] sharded down legs, out[1] gather of the first replicated right-hand side, out[2] the levels
+// below the sharded ones (both directions; on one GPU: everything), out[3] sharded up legs.
+// Collective on a sharded hierarchy (every rank runs the same cycles).
+int amgb_hierarchy_phase_times(amgb_hierarchy* h, int reps, double* out) {
+  return guarded([&] {
+    if (!h || !out || reps < 1) throw std::invalid_argument("bad argument");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    cudaEvent_t ev[5];
+    for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+    for (int k = 0; k < 4; ++k) out[k] = 0.0;
+    for (int i = 0; i < reps + 1; ++i) {
+      h->phase_ev = ev;
+      try {
+        h->enqueue_vcycle(h->stream);
+      } catch (...) {
+        h->phase_ev = nullptr;
+        throw;
+      }
+      h->phase_ev = nullptr;
+      CUDA_CHECK(cudaStreamSynchronize(h->stream));
+      if (i == 0) continue;  // warm-up
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+        out[k] += ms / reps;
+      }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    h->check_halo();
   });
 }
 

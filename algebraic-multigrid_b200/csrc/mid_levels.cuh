@@ -21,6 +21,7 @@
 // phases) so that tests/cpp/mid_levels_host.cpp runs the very same range logic serially on the
 // CPU and checks it against the oracle.
 #pragma once
+#include <cmath>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -178,10 +179,39 @@ struct Arith {
 #endif
     return sub(acc, mul(a, x));
   }
+  static AMGB_MID_FN double fma_(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return std::fma(a, b, c);
+#endif
+  }
+  // the FAST formulas are those of stream_leg.cuh, so a level gives the same bits whichever kernel runs it
   static AMGB_MID_FN double relax(double x, double r, double d, double omega) {
     if (d == 0.0) return x;
-    if (FAST) return x + (omega * rcp(d)) * r;
+    if (FAST) return fma_(omega * rcp(d), r, x);
     return add(x, mul(omega, div(r, d)));
+  }
+  // (.5 r0 + r1) + .5 r2 with absent terms passed as 0 (interpolator.hpp:64-68)
+  static AMGB_MID_FN double restrict3(double r0, bool h0, double r1, bool h1, double r2, bool h2) {
+    if (FAST) return fma_(0.5, (h0 ? r0 : 0.0) + (h2 ? r2 : 0.0), h1 ? r1 : 0.0);
+    double acc = 0.0;
+    if (h0) acc = add(acc, mul(0.5, r0));
+    if (h1) acc = add(acc, mul(1.0, r1));
+    if (h2) acc = add(acc, mul(0.5, r2));
+    return acc;
+  }
+  // u + (P e)_k: odd k: e1; even k: .5 e0 + .5 e1, absent terms passed as 0 (interpolator.hpp:52-56)
+  static AMGB_MID_FN double prolong_add(double u, bool odd, double e0, bool h0, double e1, bool h1) {
+    if (FAST) return odd ? u + (h1 ? e1 : 0.0) : fma_(0.5, (h0 ? e0 : 0.0) + (h1 ? e1 : 0.0), u);
+    double acc = 0.0;
+    if (odd) {
+      if (h1) acc = add(acc, mul(1.0, e1));
+    } else {
+      if (h0) acc = add(acc, mul(0.5, e0));
+      if (h1) acc = add(acc, mul(0.5, e1));
+    }
+    return add(u, acc);
   }
   static AMGB_MID_FN double relax_zero(double f, double d, double omega) {
     if (d == 0.0) return 0.0;
@@ -295,11 +325,10 @@ AMGB_MID_FN void run_down(const Params& P, int b, Env& env) {
     const Range cown = Q.own[i + 1];
     env.phase([&](int t, int nt) {
       for (int J = cr.lo + t; J <= cr.hi; J += nt) {
-        double acc = 0.0;
         const int k = 2 * J;
-        if (k < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, src[k - base]));
-        if (k + 1 < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(1.0, src[k + 1 - base]));
-        if (k + 2 < V.n) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, src[k + 2 - base]));
+        const bool h0 = k < V.n, h1 = k + 1 < V.n, h2 = k + 2 < V.n;
+        const double acc = Arith<FAST>::restrict3(h0 ? src[k - base] : 0.0, h0, h1 ? src[k + 1 - base] : 0.0, h1,
+                                                  h2 ? src[k + 2 - base] : 0.0, h2);
         if (Fn) Fn[J - (cr.lo & ~1)] = acc;
         if (inside(cown, J)) fg[J] = acc;
       }
@@ -333,16 +362,11 @@ AMGB_MID_FN void run_up(const Params& P, int b, Env& env) {
     // input: tmp + P e (interpolator.hpp:52-56, multigrid.hpp:294-296)
     env.phase([&](int t, int nt) {
       for (int k = inp.lo + t; k <= inp.hi; k += nt) {
-        double acc = 0.0;
         const int J = k >> 1;
         auto ev = [&](int j) { return e_global ? ld_global(e + j) : e[j - e_base]; };
-        if (k & 1) {
-          if (J < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(1.0, ev(J)));
-        } else {
-          if (J - 1 >= 0 && J - 1 < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, ev(J - 1)));
-          if (J < V.n_coarse) acc = Arith<FAST>::add(acc, Arith<FAST>::mul(0.5, ev(J)));
-        }
-        A[k - base] = Arith<FAST>::add(A[k - base], acc);
+        const bool odd = k & 1;
+        const bool h1 = J < V.n_coarse, h0 = !odd && J - 1 >= 0 && J - 1 < V.n_coarse;
+        A[k - base] = Arith<FAST>::prolong_add(A[k - base], odd, h0 ? ev(J - 1) : 0.0, h0, h1 ? ev(J) : 0.0, h1);
       }
     });
     env.sync();

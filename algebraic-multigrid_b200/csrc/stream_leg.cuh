@@ -266,8 +266,8 @@ struct Leg {
     const unsigned long long want = *epoch_word;
     const long long t0 = clock64();
     while (true) {
-      unsigned long long seen;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      // relaxed polling (no fence per poll, nothing at all for the warps that are not at the edge) ...
+      const unsigned long long seen = *reinterpret_cast<const volatile unsigned long long*>(flag);
       if (__all_sync(0xffffffffu, seen >= want)) break;
       if (__any_sync(0xffffffffu, clock64() - t0 > Y.timeout_cycles)) {  // a neighbour died or stalled
         *Y.timed_out = 1;
@@ -275,16 +275,24 @@ struct Leg {
       }
       __nanosleep(32);
     }
+    // ... and ONE acquire load once the flag is up, on the edge warps only: the neighbour's pushes
+    // (released system-wide before its flag store) are visible to the loads that follow
+    if (edge) {
+      unsigned long long seen;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+    }
   }
-  static __device__ __forceinline__ void signal_side(const Sync& Y, int side, int lane) {
-    // every lane's peer stores are fenced system-wide before lane 0 counts the warp as done
-    __threadfence_system();
+  // wrote: this warp stored into a neighbour's memory (only then its stores need the system-wide fence)
+  static __device__ __forceinline__ void signal_side(const Sync& Y, int side, int lane, bool wrote) {
+    if (wrote) __threadfence_system();
     __syncwarp();
     if (lane == 0) {
       const unsigned prev = atomicAdd(Y.done[side], 1u);
       if (prev + 1u == (unsigned)Y.expected[side]) {
-        *Y.done[side] = 0u;      // the next launch of this site starts from zero (stream order)
-        __threadfence_system();  // cumulativity: the other edge warps' stores are ordered before the flag
+        *Y.done[side] = 0u;  // the next launch of this site starts from zero (stream order)
+        // the other edge warps fenced their peer stores system-wide before counting themselves done; a
+        // device-scope fence here orders that observation before the (cumulative) release store below
+        __threadfence();
         const unsigned long long e = *Y.epoch[side] + 1ull;
         *Y.epoch[side] = e;
         if (Y.peer_flag[side] != nullptr)
@@ -293,25 +301,57 @@ struct Leg {
     }
   }
   // push the rows / coarse entries this warp stored that a neighbour keeps as ghosts: each lane
-  // re-reads what it wrote itself (L1/L2 hits) -- the hot loop carries no push code
-  static __device__ __forceinline__ void push_rows(const Params& P, int k_first, int j0, int j1, const Own& own) {
-    const Sync& Y = P.sync;
-    for (int j = j0, k = k_first; j < j1; ++j, k += P.m) {
-      if (!own(k)) continue;
+  // re-reads what it wrote itself -- the hot loop carries no push code.  Only the few lines of the
+  // chunk that intersect a push range are visited, four rows per batch so their loads overlap.
+  static __device__ __forceinline__ bool push_range(const double* src, double* dst, int k_lane, int m, int lo, int hi,
+                                                    const Own& own) {
+    // rows k = k_lane + t * m (t >= 0) of this lane inside [lo, hi) and inside what the warp stored
+    lo = max(lo, own.st_lo);
+    hi = min(hi, own.st_lo + (int)own.st_cnt);
+    if (!own.lane || hi <= lo) return false;
+    int t0 = (lo - k_lane + m - 1) / m;
+    if (lo <= k_lane) t0 = 0;
+    bool wrote = false;
+    for (int k = k_lane + t0 * m; k < hi; k += 4 * m) {
+      double v[4];
 #pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        const Push& U = Y.push_u[side];
-        if (U.dst != nullptr && k >= U.begin && k < U.end) U.dst[k] = P.uout[k];
-        if (KIND != UP) {
-          const Push& F = Y.push_fc[side];
-          const int kg = k + P.base;
-          if (F.dst != nullptr && (kg & 1)) {
-            const int Jl = ((kg - 1) >> 1) - P.cbase;
-            if (Jl >= F.begin && Jl < F.end && Jl + P.cbase < P.n_coarse) F.dst[Jl] = P.fc[Jl];
+      for (int q = 0; q < 4; ++q) v[q] = (k + q * m < hi) ? __ldcg(src + k + q * m) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (k + q * m < hi) dst[k + q * m] = v[q];
+      wrote = true;
+    }
+    return wrote;
+  }
+  static __device__ __forceinline__ bool push_rows(const Params& P, int k_first, const Own& own) {
+    const Sync& Y = P.sync;
+    bool wrote = false;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const Push& U = Y.push_u[side];
+      if (U.dst != nullptr) wrote |= push_range(P.uout, U.dst, k_first, P.m, U.begin, U.end, own);
+      if (KIND != UP) {
+        const Push& F = Y.push_fc[side];
+        if (F.dst != nullptr) {
+          // coarse entry Jl was produced by the lane that owns fine row k = 2 (Jl + cbase) + 1 - base
+          const int k_lo = 2 * (F.begin + P.cbase) + 1 - P.base, k_hi = 2 * (F.end - 1 + P.cbase) + 1 - P.base + 1;
+          const int lo = max(k_lo, own.st_lo), hi = min(k_hi, own.st_lo + (int)own.st_cnt);
+          if (own.lane && hi > lo) {
+            int t0 = (lo <= k_first) ? 0 : (lo - k_first + P.m - 1) / P.m;
+            for (int k = k_first + t0 * P.m; k < hi; k += P.m) {
+              const int kg = k + P.base;
+              if (!(kg & 1)) continue;
+              const int Jl = ((kg - 1) >> 1) - P.cbase;
+              if (Jl >= F.begin && Jl < F.end && Jl + P.cbase < P.n_coarse) {
+                F.dst[Jl] = __ldcg(P.fc + Jl);
+                wrote = true;
+              }
+            }
           }
         }
       }
     }
+    return __any_sync(0xffffffffu, wrote);
   }
 
   static __device__ __forceinline__ void run(const Params& P) {
@@ -333,25 +373,41 @@ struct Leg {
     }
     const bool edge_lo = P.sync.enabled && !dup && chunk < P.sync.edge_lo_chunks;
     const bool edge_hi = P.sync.enabled && !dup && chunk >= P.sync.edge_hi_chunk0;
-    if (P.sync.enabled) {  // kernel parameter: uniform
-      wait_side(P.sync, 0, edge_lo);
-      wait_side(P.sync, 1, edge_hi);
-    }
+    const bool waits = P.sync.enabled && !(P.sync.enabled & 2);  // kernel parameter: uniform (bits 1-3: timing experiments)
+    if (waits) wait_side(P.sync, 0, edge_lo);  // the lower ghost rows are the first thing a lower-edge warp loads
 
     State S;
 #pragma unroll
     for (int s = 0; s < NS; ++s) S.w[s][0] = S.w[s][1] = S.w[s][2] = 0.0;
     const int jA = j0 - NS;
     int k1 = jA * P.m + (i0 - H) + lane;  // this lane's row on line jA
+    int left = P.LJ + 2 * NS;  // steps jA - 1 .. j0 + LJ + NS - 2 (a short last chunk just runs past its end)
+    // The upper ghost rows are the LAST thing an upper-edge warp loads: its wait for the upper neighbour
+    // is deferred to the last ring period before the loads reach them, so the neighbour's latency
+    // hides behind the chunk's own work.  (Pushes into the neighbour happen after the wait either way.)
+    int wait_at = left;  // value of `left` at which the upper-side wait happens (period boundaries only)
+    if (waits) {
+      const int ghost_line = (P.own_end - 64) / P.m - 1;  // first line whose loads may touch rows >= own_end
+      const int steps_before = ghost_line - jA - PF;       // steps whose loads stay below it
+      if (steps_before > 0) wait_at = left - (steps_before / RS) * RS;
+      if (wait_at < 1) wait_at = left - ((left - 1) / RS) * RS;  // never later than the last period
+      if (__any_sync(0xffffffffu, wait_at == left)) wait_side(P.sync, 1, edge_hi);
+    }
 #pragma unroll
     for (int q = 0; q < PF; ++q) load(S.R[q], P, k1 + q * P.m);
-    int left = P.LJ + 2 * NS;  // steps jA - 1 .. j0 + LJ + NS - 2 (a short last chunk just runs past its end)
-    while (left > 0) steps<0>(S, P, k1, left, own);
+    const int first = left;
+    while (left > 0) {
+      // (a vote, so the compiler knows the branch is warp-uniform and keeps the shuffles below convergent)
+      if (waits && __any_sync(0xffffffffu, left == wait_at && left != first)) wait_side(P.sync, 1, edge_hi);
+      steps<0>(S, P, k1, left, own);
+    }
 
     if (edge_lo || edge_hi) {
-      push_rows(P, j0 * P.m + (i0 - H) + lane, j0, j1, own);
-      if (edge_lo) signal_side(P.sync, 0, lane);
-      if (edge_hi) signal_side(P.sync, 1, lane);
+      const bool wrote = (P.sync.enabled & 4) ? false : push_rows(P, j0 * P.m + (i0 - H) + lane, own);
+      if (!(P.sync.enabled & 8)) {
+        if (edge_lo) signal_side(P.sync, 0, lane, wrote);
+        if (edge_hi) signal_side(P.sync, 1, lane, wrote);
+      }
     }
   }
 };

@@ -312,6 +312,12 @@ int amgb_hierarchy_mid_range(const amgb_hierarchy* h, int* first, int* end, int*
  * number of entries that differ bitwise from the host-built mirror of level + 1 (0 expected). */
 int amgb_hierarchy_galerkin_device(amgb_hierarchy* h, int level, double* ms, int64_t* mismatches);
 
+/* Mean milliseconds of the four phases of a V-cycle on this rank over `reps` un-captured cycles:
+ * out[0] sharded down legs, out[1] gather of the first replicated right-hand side, out[2] the levels
+ * below the sharded ones (on one GPU: the whole cycle), out[3] sharded up legs.  Collective on a
+ * sharded hierarchy.  Advances the level state by reps + 1 cycles. */
+int amgb_hierarchy_phase_times(amgb_hierarchy* h, int reps, double* out);
+
 /* counters: kernels launched by this library in this process, and per V-cycle */
 int64_t amgb_kernel_launches(void);
 int64_t amgb_hierarchy_launches_per_vcycle(const amgb_hierarchy* h);

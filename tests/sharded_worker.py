@@ -62,7 +62,10 @@ def main():
                 single.vcycle()
             for l in range(L):
                 got, want = mg.get_soln(l), single.get_soln(l)
-                assert got.tobytes() == want.tobytes(), (n, l, use_graph, nu, fuse, np.abs(got - want).max())
+                if arith == amg.ARITH_REFERENCE:   # Jacobi is independent of the partition: same bits
+                    assert got.tobytes() == want.tobytes(), (n, l, use_graph, nu, fuse, np.abs(got - want).max())
+                else:   # fast arithmetic: a level may run in a different kernel (leg vs mid) than on one GPU
+                    assert np.linalg.norm(got - want) <= 1e-13 * np.linalg.norm(want), (n, l, use_graph)
             assert not mg.halo_timed_out()
             if legs and fused_push:   # the legs push their boundary rows themselves: no exchange launches
                 assert mg.halo_exchanges_per_vcycle() == 0, mg.halo_exchanges_per_vcycle()
@@ -70,13 +73,15 @@ def main():
             assert abs(r_sh - r_one) <= 1e-13 * r_one, (r_sh, r_one)
             # row-block getters / setters: this rank's rows only, and a cycle from the state they set
             b0, b1 = mg.local_range(0)
-            assert mg.get_soln_local(0).tobytes() == single.get_soln(0)[b0:b1].tobytes()
+            same = (lambda x, y: x.tobytes() == y.tobytes()) if arith == amg.ARITH_REFERENCE else (
+                lambda x, y: np.linalg.norm(x - y) <= 1e-13 * np.linalg.norm(y))
+            assert same(mg.get_soln_local(0), single.get_soln(0)[b0:b1])
             rng = np.random.default_rng(5)
             u_new, f_new = rng.standard_normal(n * n), rng.standard_normal(n * n)
             mg.set_soln_local(0, u_new[b0:b1]); mg.set_rhs_local(0, f_new[b0:b1])
             single.set_soln(0, u_new); single.set_rhs(0, f_new)
             mg.vcycle(); single.vcycle()
-            assert mg.get_soln_local(0).tobytes() == single.get_soln(0)[b0:b1].tobytes()
+            assert same(mg.get_soln_local(0), single.get_soln(0)[b0:b1])
             assert mg.get_rhs_local(0).tobytes() == f_new[b0:b1].tobytes()
             mg.set_soln(0, np.zeros(n * n)); mg.set_rhs(0, b)
             if rank == 0 and n <= 600 and not use_graph and arith == amg.ARITH_REFERENCE:
