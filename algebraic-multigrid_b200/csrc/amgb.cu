@@ -696,6 +696,11 @@ struct amgb_hierarchy {
   DevBuf<unsigned long long> leg_epochs;   // [leg site][side]
   DevBuf<unsigned int> leg_done;           // [leg site][side]
   bool fused_push = false;                 // the legs push their boundary rows themselves (no exchange launches)
+  // peer-memory all-gather of the first replicated right-hand side (k_allgather_push)
+  DevBuf<unsigned long long> gather_epochs;
+  DevBuf<unsigned int> gather_done;
+  dev::GatherParams gatherp{};
+  bool gather_push = false;
   // second stream: the halo exchange of a sweep runs beside the sweep of the block interior
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -743,8 +748,13 @@ struct amgb_hierarchy {
     const int G = world(), g = rank();
     // [site][bumped by lower / upper neighbour][arrived, data] of the stand-alone exchanges, then
     // [leg site][bumped by lower / upper neighbour] of the fused legs (struct sleg::Sync)
-    flags.alloc((size_t)kMaxSites * 4 + (size_t)kMaxLegSites * 2);
+    // then [source rank][arrived, data] of the peer-memory all-gather
+    flags.alloc((size_t)kMaxSites * 4 + (size_t)kMaxLegSites * 2 + 2 * 8);
     flags.zero(stream);
+    gather_epochs.alloc(8);
+    gather_epochs.zero(stream);
+    gather_done.alloc(8);
+    gather_done.zero(stream);
     leg_epochs.alloc((size_t)kMaxLegSites * 2);
     leg_epochs.zero(stream);
     leg_done.alloc((size_t)kMaxLegSites * 2);
@@ -754,8 +764,8 @@ struct amgb_hierarchy {
     CUDA_CHECK(cudaHostAlloc(&timed_out_host, sizeof(int), cudaHostAllocMapped));
     *timed_out_host = 0;
     CUDA_CHECK(cudaHostGetDevicePointer(&timed_out_dev, timed_out_host, 0));
-    // handles: per rank [flags, then u, tmp and fw of every sharded level]
-    const int per_rank = 1 + 3 * n_sharded;
+    // handles: per rank [flags, then u, tmp and fw of every sharded level, then the first replicated f]
+    const int per_rank = 2 + 3 * n_sharded;
     const size_t hb = sizeof(cudaIpcMemHandle_t);  // 64 bytes = 8 doubles
     std::vector<cudaIpcMemHandle_t> mine(per_rank);
     bool ok = cudaIpcGetMemHandle(&mine[0], flags.p) == cudaSuccess;
@@ -764,6 +774,7 @@ struct amgb_hierarchy {
       ok = ok && cudaIpcGetMemHandle(&mine[2 + 3 * l], lv[l].tmp.p) == cudaSuccess;
       ok = ok && cudaIpcGetMemHandle(&mine[3 + 3 * l], lv[l].fw.p) == cudaSuccess;
     }
+    ok = ok && cudaIpcGetMemHandle(&mine[1 + 3 * n_sharded], lv[n_sharded].f.p) == cudaSuccess;
     cudaGetLastError();
     // all-gather (handles, ok flag) through NCCL on a device staging buffer
     const size_t dbl_per_rank = per_rank * hb / sizeof(double) + 1;
@@ -807,9 +818,39 @@ struct amgb_hierarchy {
         peers[l].lo_n_own = (int)(plan.start[l][g] - plan.start[l][g - 1]);
       }
     }
+    // all-gather by peer-memory stores: every other rank's flags and first replicated right-hand side
+    bool gmapped = mapped && G - 1 <= dev::kGatherMaxPeers && G <= 8;
+    const char* gp = std::getenv("AMGB_GATHER_PUSH");
+    if (gp && std::string(gp) == "0") gmapped = false;
+    if (gmapped) {
+      gatherp = dev::GatherParams{};
+      gatherp.n_peers = G - 1;
+      gatherp.src = lv[n_sharded].f.p;
+      gatherp.begin = (int)coarse_block_start[g];
+      gatherp.count = (int)(coarse_block_start[g + 1] - coarse_block_start[g]);
+      gatherp.timed_out = timed_out_dev;
+      gatherp.timeout_cycles = halo_timeout_cycles;
+      const size_t goff = (size_t)kMaxSites * 4 + (size_t)kMaxLegSites * 2;
+      int k = 0;
+      for (int r = 0; r < G && gmapped; ++r) {
+        if (r == g) continue;
+        unsigned long long* pf = (r == g - 1) ? peer_flags_lo : (r == g + 1) ? peer_flags_hi : (unsigned long long*)open(r, 0);
+        double* pv = (double*)open(r, 1 + 3 * n_sharded);
+        gmapped = gmapped && pf && pv;
+        dev::GatherPeer& R = gatherp.peer[k];
+        R.dst = pv;
+        R.peer_flags = pf ? pf + goff + 2 * g : nullptr;
+        R.my_flags = flags.p + goff + 2 * r;
+        R.epoch = gather_epochs.p + k;
+        R.done = gather_done.p + k;
+        ++k;
+      }
+    }
     // every rank must agree, otherwise some would wait for flags nobody bumps
     scalar_host_and(mapped);
     p2p = mapped;
+    scalar_host_and(gmapped);
+    gather_push = p2p && gmapped;
     const char* fp = std::getenv("AMGB_FUSED_PUSH");
     if (p2p && !(fp && std::string(fp) == "0")) wire_leg_sync();
   }
@@ -958,6 +999,14 @@ struct amgb_hierarchy {
     }
     NCCL_CHECK(nc.GroupEnd());
   }
+  // the first replicated right-hand side: every rank gets the blocks the other ranks produced
+  void gather_coarse_rhs(cudaStream_t s) {
+    if (gather_push) {
+      LAUNCH(dev::k_allgather_push, gatherp.n_peers * dev::kGatherSlices, 512, 0, s, gatherp);
+      return;
+    }
+    allgather_blocks(lv[n_sharded].f.p, coarse_block_start, s);
+  }
   // every rank contributes its block [start[r], start[r+1]) of a full-length vector
   void allgather_blocks(double* full, const std::vector<int64_t>& start, cudaStream_t s) {
     NcclApi& nc = NcclApi::get();
@@ -1049,7 +1098,7 @@ struct amgb_hierarchy {
       const std::vector<int64_t>& cs = coarse_block_start;
       const int64_t c0 = cs[rank()], c1 = cs[rank() + 1];
       ops[l]->residual_restrict(F.u_own(), F.f.p, C.f.p + c0, C.u.p + c0, (int)(c1 - c0), s);
-      allgather_blocks(C.f.p, cs, s);
+      gather_coarse_rhs(s);
     }
   }
   // u_l = u_l + P_l u_{l+1}   (multigrid.hpp:294-296)
@@ -1499,7 +1548,7 @@ struct amgb_hierarchy {
           leg_down(l, s);
           if (!lv[l + 1].sharded) {  // first agglomerated level: every rank gets the whole right-hand side
             mark(1, s);
-            allgather_blocks(lv[l + 1].f.p, coarse_block_start, s);
+            gather_coarse_rhs(s);
             mark(2, s);
           }
         } else if (lv[l].sharded) {
@@ -1517,7 +1566,7 @@ struct amgb_hierarchy {
           }
           if (!lv[l + 1].sharded) {  // first agglomerated level: every rank gets the whole right-hand side
             mark(1, s);
-            allgather_blocks(lv[l + 1].f.p, coarse_block_start, s);
+            gather_coarse_rhs(s);
             mark(2, s);
           }
         } else {

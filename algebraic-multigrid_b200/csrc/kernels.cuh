@@ -662,6 +662,59 @@ __global__ void __launch_bounds__(1024) k_halo_exchange(HaloSide lo, HaloSide hi
   __syncthreads();
 }
 
+// ------------------------------------------------------------------ peer-memory all-gather
+// The first level below the sharded ones is replicated: every rank needs all of its right-hand side,
+// each rank having produced one block of it.  One launch: the blocks of group r (blockIdx.x / kSlices)
+// serve peer r -- ARRIVE handshake (the peer has finished every earlier kernel, so nobody still reads
+// the vector this launch overwrites), then each block stores its slice of this rank's rows straight
+// into the peer's copy over NVLink, the last one releases the DATA flag, and everybody waits for the
+// peer's own DATA flag before the launch ends.  Replaces G grouped NCCL broadcasts.
+constexpr int kGatherSlices = 4;
+constexpr int kGatherMaxPeers = 7;
+struct GatherPeer {
+  double* dst;                          // peer's copy of the vector (element 0)
+  unsigned long long* peer_flags;       // peer's flag pair for ME as the source: [0] arrived, [1] data
+  const unsigned long long* my_flags;   // my flag pair for this peer as the source
+  unsigned long long* epoch;            // launches done with this peer
+  unsigned int* done;                   // slice counter (self-resetting)
+};
+struct GatherParams {
+  int n_peers;
+  const double* src;  // my copy of the vector
+  int begin, count;   // my rows [begin, begin + count)
+  int* timed_out;
+  long long timeout_cycles;
+  GatherPeer peer[kGatherMaxPeers];
+};
+__global__ void __launch_bounds__(512) k_allgather_push(const __grid_constant__ GatherParams P) {
+  const GatherPeer& R = P.peer[blockIdx.x / kGatherSlices];
+  const int slice = blockIdx.x % kGatherSlices;
+  __shared__ unsigned long long e_sh;
+  if (threadIdx.x == 0) {
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(R.epoch) + 1ull;
+    e_sh = e;
+    if (slice == 0) flag_release(R.peer_flags + 0, e);          // I have arrived
+    flag_wait(R.my_flags + 0, e, P.timeout_cycles, P.timed_out);  // so has the peer
+  }
+  __syncthreads();
+  const int per = (P.count + kGatherSlices - 1) / kGatherSlices;
+  const int lo = P.begin + slice * per, hi = min(P.begin + P.count, lo + per);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) R.dst[i] = P.src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(R.done, 1u);
+    if (prev + 1u == (unsigned)kGatherSlices) {  // every slice is stored and fenced
+      *R.done = 0u;
+      __threadfence();
+      *R.epoch = e_sh;
+      flag_release(R.peer_flags + 1, e_sh);
+    }
+    flag_wait(R.my_flags + 1, e_sh, P.timeout_cycles, P.timed_out);  // the peer's rows have landed here
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ rss = sum (b - A u)^2
 // bhat_i accumulates from +0 in ascending column order, d = b_i - bhat_i
 // (common.hpp:21-25).  The outer sum is a fixed-shape tree (deterministic; it
