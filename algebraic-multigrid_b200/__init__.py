@@ -72,6 +72,8 @@ SIGNATURES = {
     "amgb_matrix_coloring": (_i, [_p, C.POINTER(_i), _pi]),
     "amgb_residual": (_i, [_p, _pd, _pd, _pd]),
     "amgb_rss": (_i, [_p, _pd, _pd, C.POINTER(_d)]),
+    "amgb_matrix_time": (_i, [_p, _i, _d, _i, _i, C.POINTER(_d)]),
+    "amgb_matrix_stream_bytes": (_l, [_p, _i]),
     "amgb_options_default": (None, [C.POINTER(Options)]),
     "amgb_hierarchy_create": (_i, [_i, _i, _pi, _pi, _pd, _pd, _l, C.POINTER(Options),
                                    C.POINTER(_p)]),
@@ -301,6 +303,16 @@ class DeviceMatrix:
         color = np.empty(self.A.cols, np.int32)
         _check(lib().amgb_matrix_coloring(self.h, C.byref(nc), color))
         return nc.value, color
+
+    def time_pass(self, kind, omega=2.0 / 3.0, warmup=3, reps=10):
+        """ms per launch of one Jacobi sweep (0) / colour-complete sweep (1) / residual (2) on the
+        vectors the last residual() / rss() call uploaded."""
+        ms = _d()
+        _check(lib().amgb_matrix_time(self.h, kind, omega, warmup, reps, C.byref(ms)))
+        return ms.value
+
+    def stream_bytes(self, kind):
+        return lib().amgb_matrix_stream_bytes(self.h, kind)
 
 
 def _fingerprint(A):

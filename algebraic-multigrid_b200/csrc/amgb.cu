@@ -1019,6 +1019,25 @@ struct amgb_hierarchy {
     NCCL_CHECK(nc.GroupEnd());
   }
 
+  // One damped-Jacobi sweep src -> dst of level l (halo-extended vectors); on a sharded level the halo
+  // exchange with ranks +-1 runs on the side stream beside the sweep of the block interior.
+  void jacobi_sweep(int l, double* src, double* dst, cudaStream_t s) {
+    Operator& A = *ops[l];
+    LevelState& S = lv[l];
+    const int w = S.halo_lo;  // >= half-bandwidth: rows [w, n_own - w) read no halo entry
+    if (S.sharded && overlap && aux_stream && S.n_own > 4 * w) {
+      CUDA_CHECK(cudaEventRecord(ev_fork, s));
+      CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+      exchange(l, src, aux_stream);  // enqueued first, on the high-priority stream
+      A.jacobi_rows(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, w, S.n_own - w, s);
+      CUDA_CHECK(cudaEventRecord(ev_join, aux_stream));
+      CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
+      A.jacobi_edges(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, w, w, s);
+    } else {
+      exchange(l, src, s);
+      A.jacobi(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, s);
+    }
+  }
   // smoother->smooth(A_l, u_l, f_l)   (multigrid.hpp:268-269, :300-301)
   // from_zero:   u_l is known to be zero (pre-smoothing of a coarse level, :278)
   // with_prolong: the coarse-grid correction u_l += P u_{l+1} (:294-296) has not been applied
@@ -1060,19 +1079,7 @@ struct amgb_hierarchy {
       }
       if (!done) {
         if (it == 0 && with_prolong) prolong_add(l, s);
-        const int w = S.halo_lo;  // >= half-bandwidth: rows [w, n_own - w) read no halo entry
-        if (S.sharded && overlap && aux_stream && S.n_own > 4 * w) {
-          CUDA_CHECK(cudaEventRecord(ev_fork, s));
-          CUDA_CHECK(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
-          exchange(l, src, aux_stream);  // enqueued first, on the high-priority stream
-          A.jacobi_rows(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, w, S.n_own - w, s);
-          CUDA_CHECK(cudaEventRecord(ev_join, aux_stream));
-          CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
-          A.jacobi_edges(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, w, w, s);
-        } else {
-          exchange(l, src, s);
-          A.jacobi(src + S.halo_lo, S.f.p, opt.omega, dst + S.halo_lo, s);
-        }
+        jacobi_sweep(l, src, dst, s);
       }
       std::swap(src, dst);
     }
@@ -2009,6 +2016,53 @@ int amgb_rss(amgb_matrix* A, const double* u, const double* b, double* out) {
     A->b.upload(b, A->op.n, A->stream);
     *out = matrix_rss(A);
   });
+}
+
+// Mean milliseconds per launch of one pass over the matrix on the vectors of the last call that
+// uploaded them (amgb_residual / amgb_rss): kind 0 one damped-Jacobi sweep, 1 one colour-complete
+// multicolour Gauss-Seidel sweep (every colour once), 2 one residual.  CUDA events on the handle's stream.
+int amgb_matrix_time(amgb_matrix* A, int kind, double omega, int warmup, int reps, double* ms_out) {
+  return guarded([&] {
+    if (!A || !ms_out || reps < 1 || kind < 0 || kind > 2) throw std::invalid_argument("bad argument");
+    CUDA_CHECK(cudaSetDevice(A->device));
+    cudaStream_t s = A->stream;
+    if (A->u.n != (size_t)A->op.n || A->b.n != (size_t)A->op.n)
+      throw ApiError(AMGB_ESTATE, "upload vectors first (amgb_residual / amgb_rss)");
+    if (kind == 1) A->op.ensure_colors(s);
+    double* src = A->u.p;
+    double* dst = A->r.p;
+    auto once = [&] {
+      if (kind == 0) {
+        A->op.jacobi(src, A->b.p, omega, dst, s);
+        std::swap(src, dst);
+      } else if (kind == 1) {
+        for (int c = 0; c < A->op.n_colors; ++c) A->op.color_pass(c, A->b.p, A->u.p, s);
+      } else {
+        A->op.residual(A->u.p, A->b.p, A->r.p, s);
+      }
+    };
+    for (int i = 0; i < warmup; ++i) once();
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, s));
+    for (int i = 0; i < reps; ++i) once();
+    CUDA_CHECK(cudaEventRecord(e1, s));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = (double)ms / reps;
+  });
+}
+// bytes of matrix data one pass streams: kind 0 / 2 the rows-of-A mirror, kind 1 the per-colour mirrors
+int64_t amgb_matrix_stream_bytes(amgb_matrix* A, int kind) {
+  if (!A) return -1;
+  if (kind != 1) return A->op.rows_of_A().stored_bytes();
+  int64_t total = 0;
+  for (auto& c : A->op.color_sell) total += c->stored_bytes();
+  return total;
 }
 
 // ---- hierarchy ----
@@ -3065,6 +3119,49 @@ int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level) {
 int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int reps, double* ms_out) {
   return guarded([&] {
     if (!h || !ms_out || reps < 1) throw std::invalid_argument("bad argument");
+    if (kind == 9 || kind == 11) {
+      // 9: one damped-Jacobi sweep, 11: one residual of `level`, on a sharded level INCLUDING the halo
+      // exchange with ranks +-1 (the smoother + residual microbenchmark).
+      // Collective on a sharded hierarchy.  The level's iterate is restored afterwards.
+      h->check_level(level);
+      CUDA_CHECK(cudaSetDevice(h->device));
+      cudaStream_t s = h->stream;
+      LevelState& S = h->lv[level];
+      if (!S.tmp.p) S.tmp.alloc(S.n_vec() + 8);
+      DevBuf<double> keep;
+      keep.alloc(S.u.n);
+      CUDA_CHECK(cudaMemcpyAsync(keep.p, S.u.p, sizeof(double) * S.u.n, cudaMemcpyDeviceToDevice, s));
+      double* src = S.u.p;
+      double* dst = S.tmp.p;
+      auto once = [&] {
+        h->site_cursor = amgb_hierarchy::kMaxSites - 1;  // reserved site of out-of-cycle exchanges
+        if (kind == 9) {
+          h->jacobi_sweep(level, src, dst, s);
+          std::swap(src, dst);
+        } else {
+          h->exchange(level, S.u.p, s);
+          h->ops[level]->residual(S.u_own(), S.f.p, S.tmp_own(), s);
+        }
+      };
+      for (int i = 0; i < warmup; ++i) once();
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, s));
+      for (int i = 0; i < reps; ++i) once();
+      CUDA_CHECK(cudaEventRecord(e1, s));
+      CUDA_CHECK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      CUDA_CHECK(cudaMemcpyAsync(S.u.p, keep.p, sizeof(double) * S.u.n, cudaMemcpyDeviceToDevice, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      h->site_cursor = 0;
+      h->check_halo();
+      *ms_out = (double)ms / reps;
+      return;
+    }
     if (kind >= 6 && kind <= 8) {
       // 6 / 7: the mid-level down / up kernel, 8: the coarse tail (or the coarsest solve alone).  They are
       // timed on the live level state (a cycle's worth of it): nothing to restore, every run computes

@@ -127,6 +127,14 @@ int amgb_residual(amgb_matrix* A, const double* u, const double* f, double* r);
 /* sum_i (b_i - (A u)_i)^2 (include/amg/common.hpp:17-27) */
 int amgb_rss(amgb_matrix* A, const double* u, const double* b, double* out);
 
+/* Timing hook of the smoother + residual microbenchmark: mean milliseconds
+ * per launch (CUDA events on the handle's stream) of one pass over the matrix on the vectors the
+ * last amgb_residual / amgb_rss call uploaded.  kind 0: one damped-Jacobi sweep, 1: one
+ * colour-complete multicolour Gauss-Seidel sweep, 2: one residual.  amgb_matrix_stream_bytes: the
+ * matrix bytes such a pass streams (kind 1 after the colouring exists). */
+int amgb_matrix_time(amgb_matrix* A, int kind, double omega, int warmup, int reps, double* ms_per_launch);
+int64_t amgb_matrix_stream_bytes(amgb_matrix* A, int kind);
+
 /* ------------------------------------------------------------------------
  * Hierarchy = AMG::Multigrid<double> (include/amg/multigrid.hpp:22-365).
  * ---------------------------------------------------------------------- */
@@ -338,7 +346,9 @@ int64_t amgb_hierarchy_vcycle_bytes(const amgb_hierarchy* h);
  * kind: 0 smoother pass (one Jacobi sweep / one colour-complete pass / one GS
  * direction), 1 residual, 2 residual+restrict, 3 prolong+add, 4 fused down leg,
  * 5 fused up leg (levels with amgb_hierarchy_fused_legs), 6 / 7 the mid-level down / up
- * kernel, 8 the coarse tail (level ignored for 6-8).  Runs `reps`
+ * kernel, 8 the coarse tail (level ignored for 6-8); 9 one damped-Jacobi sweep and 11 one
+ * residual of `level` INCLUDING the halo exchange with ranks +-1 on a sharded level
+ * (collective).  Runs `reps`
  * launches after `warmup`, returns the mean milliseconds per launch.
  * ---------------------------------------------------------------------- */
 int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int reps,

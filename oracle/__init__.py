@@ -321,3 +321,38 @@ class Multigrid:
         buf = np.empty(4096, np.float64)
         n = lib().orc_mg_hist(self.ptr, buf, 4096)
         return buf[:min(n, 4096)].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Full-size checker for the 8193^2 microbenchmark: the oracle's per-row arithmetic on the
+# five-point operator, vectorised with numpy (one array operation per stencil entry, in ascending
+# column order, separate multiply and subtract -- numpy never fuses them).  Bit-identical to
+# orc_residual / orc_jacobi_sweep above on the matrix orc_laplacian_aniso generates
+# (tests/test_oracle_golden.py checks that at small n); needs no 4 GB CSC matrix.
+# ---------------------------------------------------------------------------------------------
+def five_point_coefficients(n, eps_y=1.0):
+    """(cross, line, diag) = the entries at offsets -+n, -+1, 0 of orc_laplacian_aniso(n, eps_y)."""
+    h = lib().orc_grid_spacing_h(n)   # grid.hpp:31
+    hh = h * h
+    d_off, d_dia = 1.0 / hh, -2.0 / hh   # grid.hpp:62-72
+    return eps_y * d_off, d_off, d_dia + eps_y * d_dia
+
+
+def five_point_residual(n, eps_y, u, f):
+    """r = f - A u in the reference's order ((f - a1 u1) - a2 u2) - ... (multigrid.hpp:272-274)."""
+    cross, line, diag = five_point_coefficients(n, eps_y)
+    U = u.reshape(n, n)
+    acc = f.reshape(n, n).copy()
+    acc[1:, :] -= cross * U[:-1, :]      # offset -n
+    acc[:, 1:] -= line * U[:, :-1]       # offset -1
+    acc -= diag * U                      # diagonal
+    acc[:, :-1] -= line * U[:, 1:]       # offset +1
+    acc[:-1, :] -= cross * U[1:, :]      # offset +n
+    return acc.reshape(-1)
+
+
+def five_point_jacobi(n, eps_y, u, f, omega):
+    """u + omega * (r / d), the oracle's damped-Jacobi sweep (orc_jacobi_sweep)."""
+    _, _, diag = five_point_coefficients(n, eps_y)
+    r = five_point_residual(n, eps_y, u, f)
+    return u + omega * (r / diag)

@@ -197,3 +197,15 @@ def test_new_smoothers_are_consistent():
     off = dense - np.diag(np.diag(dense))
     np.testing.assert_allclose(v[red], ((b - off @ u) / np.diag(dense))[red], rtol=1e-13)
     np.testing.assert_array_equal(v[~red], u[~red])
+
+
+@pytest.mark.parametrize("n,eps", [(2, 1.0), (7, 1.0), (35, 1.0), (64, 1e-3)])
+def test_numpy_five_point_restatement_matches_the_c_oracle(n, eps):
+    """The vectorised full-size checker of the 8193^2 microbenchmark (oracle.five_point_*) is
+    bit-identical to the C oracle's residual and damped-Jacobi sweep on the generated operator."""
+    A = O.laplacian(n, eps)
+    AT = A.transpose()
+    u = np.random.default_rng(1).standard_normal(n * n)
+    f = O.rhs(n)
+    assert O.five_point_residual(n, eps, u, f).tobytes() == O.residual(A, u, f).tobytes()
+    assert O.five_point_jacobi(n, eps, u, f, 0.6).tobytes() == O.jacobi_sweep(AT, u, f, 0.6).tobytes()
