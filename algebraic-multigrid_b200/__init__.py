@@ -127,6 +127,7 @@ SIGNATURES = {
     "amgb_kernel_launches": (_l, []),
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
     "amgb_hierarchy_fused_legs": (_i, [_p, _i]),
+    "amgb_hierarchy_matrix_free": (_i, [_p, _i]),
     "amgb_hierarchy_tail_first": (_i, [_p]),
     "amgb_hierarchy_mid_range": (_i, [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "amgb_hierarchy_galerkin_device": (_i, [_p, _i, C.POINTER(_d), C.POINTER(_l)]),
@@ -693,6 +694,10 @@ class Multigrid:
     def fused_legs(self, level):
         """True when `level` runs as one fused kernel per leg (option fuse bit 2)."""
         return bool(lib().amgb_hierarchy_fused_legs(self.h, level))
+
+    def matrix_free(self, level):
+        """True when the level's fused legs run matrix-free (verified constant five-point stencil)."""
+        return bool(lib().amgb_hierarchy_matrix_free(self.h, level))
 
     def galerkin_device(self, level):
         """(kernel ms, entries differing from the host-built level + 1) of the device-side R (A P)."""

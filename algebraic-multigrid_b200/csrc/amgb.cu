@@ -597,7 +597,9 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
-  o->fuse = 1 | 4 | 16 | 32;  // zero-guess sweep, streaming legs, coarse tail, mid levels; prolongation fusion (bit 1) measured slower
+  // zero-guess sweep, streaming legs, coarse tail, mid levels, matrix-free five-point legs;
+  // prolongation fusion (bit 1) measured slower
+  o->fuse = 1 | 4 | 16 | 32 | 64;
   o->arith = AMGB_ARITH_REFERENCE;
 }
 
@@ -1165,6 +1167,7 @@ struct amgb_hierarchy {
     sleg::Params sdown{}, sup{};
     unsigned mask = 0;
     int kind_down = 0;
+    bool matrix_free = false;  // the level's operator was verified to be a constant five-point stencil
   };
   std::vector<LegLevel> legs;
   static int env_int(const char* name, int dflt) {
@@ -1204,6 +1207,36 @@ struct amgb_hierarchy {
     const bool done = sleg::dispatch(kind, mask, P, s, action, wps, fast_arith());
     if (done && action == 1) g_launches.fetch_add(1, std::memory_order_relaxed);
     return done;
+  }
+  // Matrix-free legs (option fuse bit 6): true when the mirror D (row t = global row base + t) is bit
+  // for bit the constant five-point stencil cst[] on the offsets -m, -1, 0, +1, +m (setup_dia.cuh).
+  bool check_matrix_free(const DevDia& D, int base, int n_global, int m, double (&cst)[5]) {
+    if (!(opt.fuse & 64) || D.n_diag != 5 || m < 3 || n_global < 3 * m) return false;
+    const int want[5] = {-m, -1, 0, 1, m};
+    for (int d = 0; d < 5; ++d)
+      if (D.off[d] != want[d]) return false;
+    // an interior row of the mirror gives the five coefficients
+    int64_t kg = std::max<int64_t>(base, 0);
+    kg = (kg / m + 1) * (int64_t)m + 1;
+    const int64_t t0 = kg - base;
+    if (t0 < 0 || t0 >= D.n_rows || kg >= (int64_t)n_global - m - 1) return false;
+    setup::Const5 C{};
+    for (int d = 0; d < 5; ++d)
+      CUDA_CHECK(cudaMemcpyAsync(&C.c[d], D.val.p + (size_t)d * D.ld + t0, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (int d = 0; d < 5; ++d)
+      if (C.c[d] == 0.0) return false;
+    DevBuf<int> bad;
+    bad.alloc(1);
+    bad.zero(stream);
+    LAUNCH(setup::k_check_const5, blocks_for(D.n_rows, 256), 256, 0, stream, D.val.p, D.n_rows, D.ld, base, n_global, m, C,
+           bad.p);
+    int hb = 1;
+    CUDA_CHECK(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (hb) return false;
+    for (int d = 0; d < 5; ++d) cst[d] = C.c[d];
+    return true;
   }
   void leg_down(int l, cudaStream_t s) {
     const LegLevel& G = legs[l];
@@ -1248,6 +1281,10 @@ struct amgb_hierarchy {
       int n_sm = 148;
       CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
       const LevelState& C = lv[l + 1];
+      double cst[5] = {0, 0, 0, 0, 0};
+      const bool mf = mask == sleg::kMask5 && check_matrix_free(W, (int)(S.s - S.halo_lo), (int)n[l], st.P.m, cst);
+      dummy.matrix_free = mf;
+      G.matrix_free = mf;
       auto plan = [&](int kind, int NS, int X) {
         int wps = 12;
         sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
@@ -1277,6 +1314,8 @@ struct amgb_hierarchy {
         // L2 prefetch two lines beyond the register ring pays on the HBM-bound levels (measured:
         // level 0 down leg 231 -> 197 us, profiles/r2_stream_legs.md) and costs issue slots below
         P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", S.n_vec() >= (1 << 21) ? 2 : 0);
+        P.matrix_free = mf;
+        for (int d = 0; d < 5; ++d) P.cst[d] = cst[d];
         P.finish(W.n_diag);
         return P;
       };
@@ -1306,6 +1345,10 @@ struct amgb_hierarchy {
         if (sleg_dispatch(kind_down, mask, dummy, nullptr, 0) && sleg_dispatch(sleg::UP, mask, dummy, nullptr, 0)) {
           int n_sm = 148;
           CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+          double cst[5] = {0, 0, 0, 0, 0};
+          const bool mf = mask == sleg::kMask5 && check_matrix_free(A.dia, 0, (int)n[l], st.P.m, cst);
+          dummy.matrix_free = mf;
+          G.matrix_free = mf;
           auto plan = [&](int kind, int NS, int X) {
             int wps = 12;
             sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
@@ -1335,6 +1378,8 @@ struct amgb_hierarchy {
             // L2 prefetch two lines beyond the register ring pays on the HBM-bound levels (measured:
             // level 0 down leg 231 -> 197 us, profiles/r2_stream_legs.md) and costs issue slots below
             P.l2_ahead = env_int("AMGB_SLEG_L2AHEAD", n[l] >= (1 << 21) ? 2 : 0);
+            P.matrix_free = mf;
+            for (int d = 0; d < 5; ++d) P.cst[d] = cst[d];
             P.finish(A.dia.n_diag);
             return P;
           };
@@ -2938,6 +2983,9 @@ int amgb_hierarchy_mid_range(const amgb_hierarchy* h, int* first, int* end, int*
 }
 int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level) {
   return (h && h->leg_ok(level)) ? 1 : 0;
+}
+int amgb_hierarchy_matrix_free(const amgb_hierarchy* h, int level) {
+  return (h && h->leg_ok(level) && h->legs[level].matrix_free) ? 1 : 0;
 }
 int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info) {
   return guarded([&] {

@@ -37,8 +37,32 @@ bool act(const Params& P, cudaStream_t s, int action, int* warps_per_sm) {
   return true;
 }
 
+template <int KIND, int NU, int PF, bool FAST>
+bool act_mf(const Params& P, cudaStream_t s, int action, int* warps_per_sm) {
+  auto kern = k_stream_leg_mf<KIND, NU, PF, FAST>;
+  if (action == 1) {
+    kern<<<(P.n_warps + 3) / 4, 128, 0, s>>>(P);
+    check(cudaGetLastError(), "k_stream_leg_mf launch");
+  } else if (action == 2) {
+    cudaFuncAttributes fa{};
+    check(cudaFuncGetAttributes(&fa, kern), "cudaFuncGetAttributes(k_stream_leg_mf)");
+    if (warps_per_sm) *warps_per_sm = std::min(48, std::max(1, 65536 / (std::max(fa.numRegs, 1) * 128)) * 4);
+    check(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1),
+          "cudaFuncSetAttribute(k_stream_leg_mf)");
+  }
+  return true;
+}
+
 template <int KIND, unsigned MASK, bool FAST>
 bool by_nu(const Params& P, cudaStream_t s, int action, int* wps) {
+  if constexpr (MASK == kMask5) {
+    if (P.matrix_free) {
+      const int pf = env_int("AMGB_SLEG_MF_PF", 4);
+      if (P.nu == 1) return pf == 2 ? act_mf<KIND, 1, 2, FAST>(P, s, action, wps) : act_mf<KIND, 1, 4, FAST>(P, s, action, wps);
+      if (P.nu == 2) return pf == 2 ? act_mf<KIND, 2, 2, FAST>(P, s, action, wps) : act_mf<KIND, 2, 4, FAST>(P, s, action, wps);
+      return false;
+    }
+  }
   if (P.nu == 1) return act<KIND, MASK, 1, 2, FAST>(P, s, action, wps);
   if (P.nu != 2) return false;
   // five-point up leg: three lines in flight at 12 warps/SM measured 6 % faster than two at 16

@@ -125,5 +125,26 @@ __global__ void __launch_bounds__(256) k_dia_slice(const double* __restrict__ sr
   for (int d = 0; d < nd; ++d) dst[(size_t)d * ld_dst + t] = src[(size_t)d * ld_src + r];
 }
 
+// ---- is the operator exactly a constant five-point stencil?  Row t of the mirror is global row
+// base + t of a level with n_global rows and grid lines of m rows; the entries on the offsets
+// -m, -1, 0, +1, +m must be c[0..4] wherever that neighbour exists (inside the level, and inside the
+// grid line for -1 / +1) and zero elsewhere -- compared bit for bit.  *bad != 0: it is not.
+struct Const5 {
+  double c[5];
+};
+__global__ void __launch_bounds__(256) k_check_const5(const double* __restrict__ val, int n_local, int ld, int base,
+                                                      int n_global, int m, Const5 C, int* bad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_local) return;
+  const int kg = base + t;
+  const bool in = kg >= 0 && kg < n_global;
+  const int pos = in ? kg % m : 0;
+  const bool present[5] = {in && kg >= m, in && pos != 0, in, in && pos != m - 1, in && kg < n_global - m};
+  for (int d = 0; d < 5; ++d) {
+    const double want = present[d] ? C.c[d] : 0.0;
+    if (__double_as_longlong(val[(size_t)d * ld + t]) != __double_as_longlong(want)) *bad = 1;
+  }
+}
+
 }  // namespace setup
 }  // namespace amgb

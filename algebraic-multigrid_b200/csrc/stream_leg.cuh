@@ -57,8 +57,10 @@ __device__ __forceinline__ double rcp_refined(double d) {
   return __fma_rn(r, e, r);
 }
 
-template <int KIND, unsigned MASK, int NU, int PF_, bool FAST>
+// MF: matrix-free five-point operator (Params::cst, presence of a neighbour decided from the row index)
+template <int KIND, unsigned MASK, int NU, int PF_, bool FAST, bool MF = false>
 struct Leg {
+  static_assert(!MF || MASK == kMask5, "the matrix-free variant is the five-point stencil");
   static constexpr int ND = popc9(MASK);
   static constexpr int NS = stages(KIND, NU);                // chained stencil stages
   static constexpr int H = lost_lanes(KIND, NU);             // lanes lost on each side
@@ -69,9 +71,22 @@ struct Leg {
   static_assert((MASK >> 4) & 1u, "the diagonal must be present");
 
   struct Line {
-    double a[ND];
+    double a[MF ? 1 : ND];  // operator row (not loaded by the matrix-free variant)
     double f, u, e0, e1;
   };
+  // per-lane constants of the matrix-free variant: the -1 / +1 neighbours exist unless the row is the
+  // first / last of its grid line -- (k + base) mod m, the same for every row a lane visits
+  struct Lane {
+    double a_left, a_right, w;  // w = omega / diag (fast arithmetic)
+  };
+  // operator row of global row kg, entries in ascending column order: -m, -1, 0, +1, +m
+  static __device__ __forceinline__ void mf_row(const Params& P, const Lane& Z, int kg, double (&a)[5]) {
+    a[0] = (kg >= P.m) ? P.cst[0] : 0.0;
+    a[1] = Z.a_left;
+    a[2] = P.cst[2];
+    a[3] = Z.a_right;
+    a[4] = (kg < P.n_global - P.m) ? P.cst[4] : 0.0;
+  }
 
   // ---- arithmetic ----
   static __device__ __forceinline__ double mulsub(double acc, double a, double x) {
@@ -100,8 +115,10 @@ struct Leg {
   // loads of the line whose row on this lane is k (clamped to the rows that exist)
   static __device__ __forceinline__ void load(Line& L, const Params& P, int k) {
     const int kc = min(max(k, P.row_lo), P.row_hi1);
+    if constexpr (!MF) {
 #pragma unroll
-    for (int d = 0; d < ND; ++d) L.a[d] = __ldg(P.vd[d] + kc);
+      for (int d = 0; d < ND; ++d) L.a[d] = __ldg(P.vd[d] + kc);
+    }
     L.f = __ldg(P.f + kc);
     if (KIND != DOWN_ZERO) L.u = __ldg(P.uin + kc);
     if (KIND == UP) {
@@ -118,8 +135,10 @@ struct Leg {
   // no registers, the later LDG then hits L2 (lower latency = fewer lines needed in flight)
   static __device__ __forceinline__ void prefetch(const Params& P, int k) {
     const int kc = min(max(k, P.row_lo), P.row_hi1);
+    if constexpr (!MF) {
 #pragma unroll
-    for (int d = 0; d < ND; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.vd[d] + kc));
+      for (int d = 0; d < ND; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.vd[d] + kc));
+    }
     asm volatile("prefetch.global.L2 [%0];" ::"l"(P.f + kc));
     if (KIND != DOWN_ZERO) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.uin + kc));
   }
@@ -127,7 +146,7 @@ struct Leg {
   // input value of a row (stage 0); kg = global row
   static __device__ __forceinline__ double input(const Line& L, const Params& P, int kg) {
     if (KIND == DOWN_U) return L.u;
-    if (KIND == DOWN_ZERO) return relax_zero(L.f, L.a[DC], P.omega);
+    if (KIND == DOWN_ZERO) return relax_zero(L.f, MF ? P.cst[2] : L.a[MF ? 0 : DC], P.omega);
     const int Jl = (kg >> 1) - P.cbase;
     const bool odd = kg & 1;
     const double e1 = e_exists(P, Jl) ? L.e1 : 0.0;
@@ -146,8 +165,8 @@ struct Leg {
     }
   }
 
-  template <int SL>
-  static __device__ __forceinline__ void slot(const Line& L, double xm, double x0, double xp, double& acc) {
+  template <int SL, class Row>
+  static __device__ __forceinline__ void slot(const Row& a_row, double xm, double x0, double xp, double& acc) {
     if constexpr ((MASK >> SL) & 1u) {
       constexpr int d = popc9(MASK & ((1u << SL) - 1u));
       constexpr int a = SL / 3 - 1, dl = SL % 3 - 1;
@@ -156,22 +175,33 @@ struct Leg {
       if constexpr (dl < 0) xv = __shfl_up_sync(0xffffffffu, xl, 1);
       if constexpr (dl > 0) xv = __shfl_down_sync(0xffffffffu, xl, 1);
       // an absent entry is stored as 0.0 and every x is finite, so acc - 0 * x == acc: no test, no select
-      acc = mulsub(acc, L.a[d], xv);
+      acc = mulsub(acc, a_row[d], xv);
     }
   }
   // f - sum a x over the row, ascending column order
-  static __device__ __forceinline__ double stencil(const Line& L, double xm, double x0, double xp) {
-    double acc = L.f;
-    slot<0>(L, xm, x0, xp, acc);
-    slot<1>(L, xm, x0, xp, acc);
-    slot<2>(L, xm, x0, xp, acc);
-    slot<3>(L, xm, x0, xp, acc);
-    slot<4>(L, xm, x0, xp, acc);
-    slot<5>(L, xm, x0, xp, acc);
-    slot<6>(L, xm, x0, xp, acc);
-    slot<7>(L, xm, x0, xp, acc);
-    slot<8>(L, xm, x0, xp, acc);
+  template <class Row>
+  static __device__ __forceinline__ double stencil_row(double f, const Row& a_row, double xm, double x0, double xp) {
+    double acc = f;
+    slot<0>(a_row, xm, x0, xp, acc);
+    slot<1>(a_row, xm, x0, xp, acc);
+    slot<2>(a_row, xm, x0, xp, acc);
+    slot<3>(a_row, xm, x0, xp, acc);
+    slot<4>(a_row, xm, x0, xp, acc);
+    slot<5>(a_row, xm, x0, xp, acc);
+    slot<6>(a_row, xm, x0, xp, acc);
+    slot<7>(a_row, xm, x0, xp, acc);
+    slot<8>(a_row, xm, x0, xp, acc);
     return acc;
+  }
+  static __device__ __forceinline__ double stencil(const Line& L, const Params& P, const Lane& Z, int kg, double xm,
+                                                   double x0, double xp) {
+    if constexpr (MF) {
+      double a[5];
+      mf_row(P, Z, kg, a);
+      return stencil_row(L.f, a, xm, x0, xp);
+    } else {
+      return stencil_row(L.f, L.a, xm, x0, xp);
+    }
   }
 
   struct State {
@@ -206,7 +236,7 @@ struct Leg {
   // One step: loads of line jj + 1 + PF, input stage on line jj + 1 (ring slot P_), stage s on
   // line jj - s + 1 (slot P_ - s), restriction of the residual line.  k1 = this lane's row on line jj + 1.
   template <int P_>
-  static __device__ __forceinline__ void step(State& S, const Params& P, int k1, const Own& own) {
+  static __device__ __forceinline__ void step(State& S, const Params& P, int k1, const Own& own, const Lane& Z) {
     const int m = P.m;
     load(S.R[(P_ + PF) % RS], P, k1 + PF * m);
     if (P.l2_ahead > 0) prefetch(P, k1 + (PF + P.l2_ahead) * m);
@@ -221,7 +251,7 @@ struct Leg {
     for (int s = 1; s <= NS; ++s) {
       const Line& L = S.R[(P_ - s + 2 * RS) % RS];
       const int k = k1 - s * m;
-      const double acc = stencil(L, S.w[s - 1][WM(P_)], S.w[s - 1][W0(P_)], S.w[s - 1][WP(P_)]);
+      const double acc = stencil(L, P, Z, k + P.base, S.w[s - 1][WM(P_)], S.w[s - 1][W0(P_)], S.w[s - 1][WP(P_)]);
       if (KIND != UP && s == NS) {
         // residual -> restriction: f_c[J] = (.5 r[2J] + r[2J+1]) + .5 r[2J+2]   (interpolator.hpp:64-68)
         const double rm = __shfl_up_sync(0xffffffffu, acc, 1);
@@ -235,7 +265,9 @@ struct Leg {
           }
         }
       } else {
-        const double out = relax(S.w[s - 1][W0(P_)], acc, L.a[DC], P.omega);
+        double out;
+        if constexpr (MF && FAST) out = __fma_rn(Z.w, acc, S.w[s - 1][W0(P_)]);  // omega / diag is one constant
+        else out = relax(S.w[s - 1][W0(P_)], acc, MF ? P.cst[2] : L.a[MF ? 0 : DC], P.omega);
         if (s < NS) push(S.w[s], out, P_);
         if (s == S_OUT && own(k)) P.uout[k] = out;
       }
@@ -246,13 +278,13 @@ struct Leg {
   // do and is the same for every lane of the warp, so control flow stays convergent and the
   // shuffles need no re-convergence code.
   template <int P_>
-  static __device__ __forceinline__ void steps(State& S, const Params& P, int& k1, int& left, const Own& own) {
+  static __device__ __forceinline__ void steps(State& S, const Params& P, int& k1, int& left, const Own& own, const Lane& Z) {
     if constexpr (P_ < RS) {
       if (left <= 0) return;
-      step<P_>(S, P, k1, own);
+      step<P_>(S, P, k1, own, Z);
       --left;
       k1 += P.m;
-      steps<P_ + 1>(S, P, k1, left, own);
+      steps<P_ + 1>(S, P, k1, left, own, Z);
     }
   }
 
@@ -381,6 +413,14 @@ struct Leg {
     for (int s = 0; s < NS; ++s) S.w[s][0] = S.w[s][1] = S.w[s][2] = 0.0;
     const int jA = j0 - NS;
     int k1 = jA * P.m + (i0 - H) + lane;  // this lane's row on line jA
+    Lane Z{};
+    if constexpr (MF) {
+      int pos = (i0 - H + lane + P.base) % P.m;  // position of this lane's rows in their grid line
+      if (pos < 0) pos += P.m;
+      Z.a_left = (pos != 0) ? P.cst[1] : 0.0;
+      Z.a_right = (pos != P.m - 1) ? P.cst[3] : 0.0;
+      Z.w = P.omega * rcp_refined(P.cst[2]);
+    }
     int left = P.LJ + 2 * NS;  // steps jA - 1 .. j0 + LJ + NS - 2 (a short last chunk just runs past its end)
     // The upper ghost rows are the LAST thing an upper-edge warp loads: its wait for the upper neighbour
     // is deferred to the last ring period before the loads reach them, so the neighbour's latency
@@ -399,7 +439,7 @@ struct Leg {
     while (left > 0) {
       // (a vote, so the compiler knows the branch is warp-uniform and keeps the shuffles below convergent)
       if (waits && __any_sync(0xffffffffu, left == wait_at && left != first)) wait_side(P.sync, 1, edge_hi);
-      steps<0>(S, P, k1, left, own);
+      steps<0>(S, P, k1, left, own, Z);
     }
 
     if (edge_lo || edge_hi) {
@@ -416,6 +456,12 @@ template <int KIND, unsigned MASK, int NU, int PF_, bool FAST>
 __global__ void __launch_bounds__(128, (popc9(MASK) <= 5 && PF_ == 2) ? 4 : 3)
     k_stream_leg(const __grid_constant__ Params P) {
   Leg<KIND, MASK, NU, PF_, FAST>::run(P);
+}
+// matrix-free five-point legs: no operator row in the register ring, so more lines in flight and more
+// resident warps
+template <int KIND, int NU, int PF_, bool FAST>
+__global__ void __launch_bounds__(128, 6) k_stream_leg_mf(const __grid_constant__ Params P) {
+  Leg<KIND, kMask5, NU, PF_, FAST, true>::run(P);
 }
 
 }  // namespace sleg

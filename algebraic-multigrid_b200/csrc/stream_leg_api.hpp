@@ -77,6 +77,10 @@ struct Params {
   int row_lo, row_hi1;  // local rows that exist: [row_lo, row_hi1] = window ∩ level (loads are clamped to it)
   int e_lo, e_cnt;      // local coarse indices that exist: [e_lo, e_lo + e_cnt)
   int l2_ahead;         // > 0: prefetch the line this many steps beyond the register ring into L2
+  // matrix-free five-point variant (the operator was VERIFIED to be cst[] on the five offsets -m, -1,
+  // 0, +1, +m wherever the neighbour exists and empty elsewhere): no operator row is loaded
+  int matrix_free;
+  double cst[5];
   double omega;
   const double* val;
   const double* vd[9];  // val + d * ld
@@ -112,6 +116,7 @@ __host__ __device__ constexpr int lost_lanes(int kind, int nu) { return stages(k
 // `s` (returns true when a kernel was launched).  2: set the L1 carve-out (outside stream capture)
 // and report the resident warps per SM the register count allows in *warps_per_sm.
 // fast: AMGB_ARITH_FAST kernels (FMA + refined reciprocal) instead of the reference-order ones.
+// Params::matrix_free selects the matrix-free five-point kernels (kMask5 only).
 bool dispatch(int kind, unsigned mask, const Params& P, cudaStream_t s, int action, int* warps_per_sm, bool fast);
 
 }  // namespace sleg

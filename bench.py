@@ -419,16 +419,38 @@ def run_b200(a):
     survey0 = mg.pass_bytes(0)
     fused0 = mg.fused_legs(0)
     per_kernel = {}
+
+    def mat_bytes(l):
+        """operator bytes a leg of level l streams: none when the level runs matrix-free"""
+        return 0 if mg.matrix_free(l) else mg.matrix_bytes(l)
+
+    legs_timed = []
     if fused0:
-        # fused down leg of level 0 (sweeps + residual + restriction in one pass): operator,
-        # f and u read once, smoothed u written once, coarse rhs written once
-        kern_ms = mg.time_kernel(0, 4, warmup=3, reps=20)
-        bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0) + 8 * ((r1 - r0) // 2)   # this rank's row block
-        plan = mg.leg_plan(0)
+        # Fused legs (one pass per level and leg).  Algorithmic bytes of a leg on this rank's rows:
+        # operator (unless matrix-free) + f + input read + result written (+ coarse rhs / correction);
+        # the dominant kernel of the cycle is the slowest of the legs of the three finest levels.
+        for l in range(min(3, levels - 1)):
+            if not mg.fused_legs(l):
+                break
+            a0, a1 = mg.local_range(l)
+            rows = a1 - a0
+            for kind, nm in ((4, "down"), (5, "up")):
+                t_ms = mg.time_kernel(l, kind, warmup=3, reps=20)
+                alg = mat_bytes(l) + ((24 if (l == 0 or kind == 5) else 16) * rows) + 8 * (rows // 2)
+                legs_timed.append({"level": l, "leg": nm, "ms": t_ms, "algorithmic_bytes": alg,
+                                   "GB/s": alg / (t_ms * 1e-3) / 1e9, "frac": alg / (t_ms * 1e-3) / 1e9 / peak,
+                                   "matrix_free": bool(mg.matrix_free(l))})
+        top = max(legs_timed, key=lambda x: x["ms"])
+        kern_ms, bytes0 = top["ms"], top["algorithmic_bytes"]
+        plan = mg.leg_plan(top["level"], up=(top["leg"] == "up"))
         kname = "k_stream_leg" if plan["smem_bytes"] == 0 else "k_fused_leg"
-        traffic_key = kname + ("_fast" if arith == amg.ARITH_FAST else "")
-        kdesc = "%s down leg (level 0: %d Jacobi sweeps + residual + restriction in one pass, %s layout, %s arithmetic)" % (
-            kname, smoother.n_iters, mg.format(0), "fast" if arith == amg.ARITH_FAST else "reference-order")
+        traffic_key = "%s_L%d_%s%s" % (kname, top["level"], top["leg"], "_fast" if arith == amg.ARITH_FAST else "")
+        kdesc = "%s %s leg of level %d (%s; %s arithmetic, %s)" % (
+            kname, top["leg"], top["level"],
+            "%d Jacobi sweeps + residual + restriction in one pass" % smoother.n_iters if top["leg"] == "down"
+            else "prolongation + add + %d Jacobi sweeps in one pass" % smoother.n_iters,
+            "fast" if arith == amg.ARITH_FAST else "reference-order",
+            "matrix-free five-point stencil" if top["matrix_free"] else mg.format(top["level"]) + " layout")
     else:
         kern_ms = mg.time_kernel(0, 0, warmup=3, reps=20)
         bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0)       # this rank's row block
@@ -450,6 +472,7 @@ def run_b200(a):
                             "(SURVEY.md 8d): GB/s is reported for completeness")
     if plan:
         roofline["tiling"] = plan
+        roofline["legs"] = legs_timed
     pass0 = mg.matrix_bytes(0) + 24 * (r1 - r0)
     kinds = [(0, "smoother_sweep"), (1, "residual"), (2, "residual_restrict"), (3, "prolong_add")]
     if fused0:
@@ -457,7 +480,7 @@ def run_b200(a):
     for kind, nm in kinds if world == 1 else ():
         t_ms = mg.time_kernel(0, kind, warmup=3, reps=20)
         alg = {0: pass0, 1: pass0, 2: mg.matrix_bytes(0) + 16 * N0 + 8 * n1, 3: 8 * n1 + 16 * N0,
-               4: mg.matrix_bytes(0) + 24 * N0 + 8 * n1, 5: mg.matrix_bytes(0) + 24 * N0 + 8 * n1}[kind]
+               4: mat_bytes(0) + 24 * N0 + 8 * n1, 5: mat_bytes(0) + 24 * N0 + 8 * n1}[kind]
         per_kernel[nm] = {"ms": t_ms, "GB/s": alg / (t_ms * 1e-3) / 1e9,
                           "frac": alg / (t_ms * 1e-3) / 1e9 / peak}
     # bytes one V-cycle must move with the layouts and kernels in use
@@ -466,8 +489,8 @@ def run_b200(a):
     for l in range(levels - 1):
         nl, nn = mg.get_n_dofs(l), mg.get_n_dofs(l + 1)
         if mg.fused_legs(l):
-            down = mg.matrix_bytes(l) + (24 if l == 0 else 16) * nl + 8 * nn
-            up = mg.matrix_bytes(l) + 24 * nl + 8 * nn
+            down = mat_bytes(l) + (24 if l == 0 else 16) * nl + 8 * nn
+            up = mat_bytes(l) + 24 * nl + 8 * nn
             layout_bytes += down + up
         else:
             layout_bytes += (passes + 1) * (mg.matrix_bytes(l) + 24 * nl) + 24 * nl + 16 * nn
@@ -530,6 +553,8 @@ def run_b200(a):
                    "mdof_per_s": vps * N0 / 1e6, "setup_s": setup_s, "generate_s": generate_s,
                    "rss_after_timed_cycles": rss_after,
                    "fused_legs": [bool(mg.fused_legs(l)) for l in range(levels - 1)], "tail_first": mg.tail_first(),
+                   "matrix_free_levels": [l for l in range(levels - 1) if mg.matrix_free(l)],
+                   "mid_levels": list(mg.mid_range()),
                    "launches_per_vcycle": mg.launches_per_vcycle(),
                    "vcycle_layout_bytes": layout_bytes,
                    "vcycle_hbm_frac": (layout_bytes / (ms / a.steps * 1e-3) / 1e9 / peak) if world == 1 else None,

@@ -167,7 +167,12 @@ typedef struct amgb_options {
                                (default on): the mid levels between the streamed ones and
                                that tail run all their down legs in one launch and all
                                their up legs in another (shared-memory tiles with
-                               recomputed halos, mid_levels.cuh).  The arithmetic, hence
+                               recomputed halos, mid_levels.cuh); bit 6 (default on): a
+                               level whose operator is VERIFIED at setup (bit for bit, on
+                               the device) to be a constant five-point stencil runs
+                               matrix-free legs: the coefficients travel as kernel
+                               parameters and no operator row is read (28 instead of 68
+                               bytes per row).  The arithmetic, hence
                                every bit of the result, is unchanged                      */
   int arith;                /* arithmetic of the damped-Jacobi cycle's kernels.
                                AMGB_ARITH_REFERENCE (default): the oracle's operation order,
@@ -307,6 +312,8 @@ int amgb_coarse_solve(amgb_hierarchy* h);
  * (= CTAs), strips, TMA lines in flight, threads per CTA, dynamic shared memory bytes, chained
  * stencil stages. */
 int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level);
+/* 1 when the level's fused legs run matrix-free (option fuse bit 6, operator verified at setup) */
+int amgb_hierarchy_matrix_free(const amgb_hierarchy* h, int level);
 /* first level of the coarse tail that runs in one launch (option fuse bit 4), -1 if none */
 int amgb_hierarchy_tail_first(const amgb_hierarchy* h);
 int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info);

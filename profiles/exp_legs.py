@@ -19,19 +19,23 @@ while sizes[-1] > 200:
     sizes.append(amg.lib().amgb_n_H_dofs_from_n_h_dofs(sizes[-1]))
 L = len(sizes)
 A, b = amg.Grid.laplacian(n), amg.Grid.rhs(n)
-KNOBS = ("AMGB_SLEG_L2AHEAD", "AMGB_SLEG_PF", "AMGB_SLEG_WARPS_PER_SM", "AMGB_TAIL_ROWS", "AMGB_HOST_SETUP",
+KNOBS = ("AMGB_SLEG_MF_PF", "AMGB_SLEG_L2AHEAD", "AMGB_SLEG_PF", "AMGB_SLEG_WARPS_PER_SM", "AMGB_TAIL_ROWS", "AMGB_HOST_SETUP",
          "AMGB_ARITH", "AMGB_MID_ROWS", "AMGB_SLEG_MINLINES")
 for setting in settings:
     for k in KNOBS:
         os.environ.pop(k, None)
     arith = amg.ARITH_FAST
+    fuse = None
     for kv in filter(None, setting.split(",")):
         k, v = kv.split("=")
         if k == "AMGB_ARITH":
             arith = amg.ARITH_FAST if v == "fast" else amg.ARITH_REFERENCE
+        if k == "FUSE":
+            fuse = int(v)
+            continue
         os.environ[k] = v
     t0 = time.perf_counter()
-    mg = amg.Multigrid(None, amg.DampedJacobi(2.0 / 3.0, 2), A, b, L, 1e-9, 1, 1, arith=arith)
+    mg = amg.Multigrid(None, amg.DampedJacobi(2.0 / 3.0, 2), A, b, L, 1e-9, 1, 1, arith=arith, fuse=fuse)
     setup = time.perf_counter() - t0
     for _ in range(5):
         mg.vcycle()

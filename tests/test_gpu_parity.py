@@ -745,3 +745,35 @@ def test_mid_levels_are_bit_identical(monkeypatch, n, L, eps, nu, tail_rows, fus
         assert mid.get_rhs(l).tobytes() == mo.f(l).tobytes(), l
     plain.vcycle()
     assert mid.launches_per_vcycle() < plain.launches_per_vcycle()
+
+
+# ----------------------------------------------------------------- matrix-free five-point legs (fuse bit 6)
+@pytest.mark.parametrize("n,L,eps,nu", [(100, 9, 1.0, 2), (129, 10, 1e-3, 2), (257, 13, 1.0, 1), (513, 14, 1.0, 2)])
+def test_matrix_free_legs_are_bit_identical(n, L, eps, nu):
+    """Level 0 is verified at setup to be a constant five-point stencil and runs legs that read no
+    operator row; every level's iterate and right-hand side stay bit-identical to the oracle."""
+    sm = amg.DampedJacobi(2.0 / 3.0, nu)
+    mf, mo, _ = make_pair(n, L, sm, eps, fuse=1 | 4 | 64)
+    plain, _, _ = make_pair(n, L, sm, eps, fuse=1 | 4)
+    assert mf.fused_legs(0) and mf.matrix_free(0) and not mf.matrix_free(1)
+    assert plain.fused_legs(0) and not plain.matrix_free(0)
+    for _ in range(3):
+        mf.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert mf.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert mf.get_rhs(l).tobytes() == mo.f(l).tobytes(), l
+
+
+def test_matrix_free_needs_an_exactly_constant_stencil():
+    """One perturbed coefficient and the verification refuses: the general legs run (and stay exact)."""
+    n, L = 129, 10
+    A, b, _ = problem(n)
+    A.val[A.colptr[5000] + 2] *= 1.0 + 2.0 ** -40     # one diagonal entry
+    sm = amg.DampedJacobi(2.0 / 3.0, 2)
+    mg = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1, fuse=1 | 4 | 64)
+    assert mg.fused_legs(0) and not mg.matrix_free(0)
+    mo = O.Multigrid(O.Csc.from_arrays(A.rows, A.cols, A.colptr, A.rowidx, A.val), b, L, 1e-9, 1, 1,
+                     O.SMOOTHER_JACOBI, 2, 2.0 / 3.0)
+    for _ in range(2):
+        mg.vcycle(); mo.vcycle()
+    assert rel(mg.get_soln(0), mo.u(0)) <= RTOL
