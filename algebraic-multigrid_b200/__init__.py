@@ -128,6 +128,7 @@ SIGNATURES = {
     "amgb_hierarchy_launches_per_vcycle": (_l, [_p]),
     "amgb_hierarchy_fused_legs": (_i, [_p, _i]),
     "amgb_hierarchy_matrix_free": (_i, [_p, _i]),
+    "amgb_hierarchy_dictionary_types": (_i, [_p, _i]),
     "amgb_hierarchy_tail_first": (_i, [_p]),
     "amgb_hierarchy_mid_range": (_i, [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "amgb_hierarchy_galerkin_device": (_i, [_p, _i, C.POINTER(_d), C.POINTER(_l)]),
@@ -698,6 +699,10 @@ class Multigrid:
     def matrix_free(self, level):
         """True when the level's fused legs run matrix-free (verified constant five-point stencil)."""
         return bool(lib().amgb_hierarchy_matrix_free(self.h, level))
+
+    def dictionary_types(self, level):
+        """Distinct operator rows when the level's legs run from a row-type dictionary, else 0."""
+        return lib().amgb_hierarchy_dictionary_types(self.h, level)
 
     def galerkin_device(self, level):
         """(kernel ms, entries differing from the host-built level + 1) of the device-side R (A P)."""

@@ -597,9 +597,10 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
-  // zero-guess sweep, streaming legs, coarse tail, mid levels, matrix-free five-point legs;
+  // zero-guess sweep, streaming legs, coarse tail, mid levels, matrix-free five-point legs, row-type
+  // dictionary legs;
   // prolongation fusion (bit 1) measured slower
-  o->fuse = 1 | 4 | 16 | 32 | 64;
+  o->fuse = 1 | 4 | 16 | 32 | 64 | 128;
   o->arith = AMGB_ARITH_REFERENCE;
 }
 
@@ -1168,6 +1169,10 @@ struct amgb_hierarchy {
     unsigned mask = 0;
     int kind_down = 0;
     bool matrix_free = false;  // the level's operator was verified to be a constant five-point stencil
+    // row-type dictionary (option fuse bit 7): one byte per row + the table of the level's distinct rows
+    int dict_types = 0;
+    DevBuf<unsigned char> tid;
+    DevBuf<double> table;
   };
   std::vector<LegLevel> legs;
   static int env_int(const char* name, int dflt) {
@@ -1238,6 +1243,58 @@ struct amgb_hierarchy {
     for (int d = 0; d < 5; ++d) cst[d] = C.c[d];
     return true;
   }
+  // Row-type dictionary of a DIA mirror (option fuse bit 7): at most 256 distinct rows, every row
+  // verified bit for bit against its table row.  Returns the number of types (0: not applicable).
+  int build_dictionary(const DevDia& D, DevBuf<unsigned char>& tid, DevBuf<double>& table) {
+    if (!(opt.fuse & 128) || D.n_rows < 1 || D.n_diag < 1) return 0;
+    cudaStream_t s = stream;
+    const int n = D.n_rows, nd = D.n_diag;
+    DevBuf<unsigned long long> keys;
+    keys.alloc(setup::kDictSlots);
+    keys.zero(s);
+    DevBuf<int> rep, flag;
+    std::vector<int> hrep(setup::kDictSlots, 0x7fffffff);
+    rep.upload(hrep, s);
+    flag.alloc(1);
+    flag.zero(s);
+    LAUNCH(setup::k_dict_insert, blocks_for(n, 256), 256, 0, s, D.val.p, n, D.ld, nd, keys.p, rep.p, flag.p);
+    int hflag = 0;
+    CUDA_CHECK(cudaMemcpyAsync(hrep.data(), rep.p, hrep.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(&hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (hflag) return 0;
+    std::vector<std::pair<int, int>> used;  // (representative row, slot): ids in order of first appearance
+    for (int k = 0; k < setup::kDictSlots; ++k)
+      if (hrep[k] != 0x7fffffff) used.emplace_back(hrep[k], k);
+    if (used.empty() || used.size() > 256) return 0;
+    std::sort(used.begin(), used.end());
+    std::vector<short> slot_id(setup::kDictSlots, -1);
+    std::vector<int> rep_of_id(used.size());
+    for (size_t i = 0; i < used.size(); ++i) {
+      slot_id[used[i].second] = (short)i;
+      rep_of_id[i] = used[i].first;
+    }
+    const int T = (int)used.size();
+    DevBuf<short> d_slot_id;
+    d_slot_id.upload(slot_id, s);
+    DevBuf<int> d_rep;
+    d_rep.upload(rep_of_id, s);
+    table.alloc((size_t)T * nd);
+    tid.alloc((size_t)n + 8);
+    tid.zero(s);
+    LAUNCH(setup::k_dict_table, blocks_for(T * nd, 256), 256, 0, s, D.val.p, D.ld, nd, d_rep.p, T, table.p);
+    flag.zero(s);
+    LAUNCH(setup::k_dict_assign, blocks_for(n, 256), 256, 0, s, D.val.p, n, D.ld, nd, keys.p, d_slot_id.p, table.p, tid.p,
+           flag.p);
+    CUDA_CHECK(cudaMemcpyAsync(&hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (hflag) {
+      table.release();
+      tid.release();
+      return 0;
+    }
+    return T;
+  }
   void leg_down(int l, cudaStream_t s) {
     const LegLevel& G = legs[l];
     if (G.stream) sleg_dispatch(G.kind_down, G.mask, G.sdown, s, 1);
@@ -1253,7 +1310,10 @@ struct amgb_hierarchy {
   //   fuse bit 2: register-streaming legs for 3 x 3 line stencils (one or two sweeps per smooth call)
   //   fuse bit 3: TMA-ring legs for the other banded levels
   void prepare_legs(int l) {
-    if ((int)legs.size() != L) legs.assign(L, LegLevel());
+    if ((int)legs.size() != L) {
+      legs.clear();
+      legs.resize(L);
+    }
     if ((int)leg_side.size() != L) leg_side.assign(L, 0);
     LegLevel& G = legs[l];
     G.ok = false;
@@ -1285,11 +1345,16 @@ struct amgb_hierarchy {
       const bool mf = mask == sleg::kMask5 && check_matrix_free(W, (int)(S.s - S.halo_lo), (int)n[l], st.P.m, cst);
       dummy.matrix_free = mf;
       G.matrix_free = mf;
+      G.dict_types = mf ? 0 : build_dictionary(W, G.tid, G.table);
+      dummy.dict_types = G.dict_types;
       auto plan = [&](int kind, int NS, int X) {
         int wps = 12;
         sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
         const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", wps);
         sleg::Params P{};
+        P.dict_types = G.dict_types;
+        P.tid = G.tid.p;
+        P.table = G.table.p;
         P.nu = nu;
         P.base = (int)(S.s - S.halo_lo);
         P.n_global = (int)n[l];
@@ -1349,11 +1414,16 @@ struct amgb_hierarchy {
           const bool mf = mask == sleg::kMask5 && check_matrix_free(A.dia, 0, (int)n[l], st.P.m, cst);
           dummy.matrix_free = mf;
           G.matrix_free = mf;
+          G.dict_types = mf ? 0 : build_dictionary(A.dia, G.tid, G.table);
+          dummy.dict_types = G.dict_types;
           auto plan = [&](int kind, int NS, int X) {
             int wps = 12;
             sleg_dispatch(kind, mask, dummy, nullptr, 2, &wps);
             const int warps_target = n_sm * env_int("AMGB_SLEG_WARPS_PER_SM", wps);
             sleg::Params P{};
+            P.dict_types = G.dict_types;
+            P.tid = G.tid.p;
+            P.table = G.table.p;
             P.nu = nu;
             P.base = 0;
             P.n_global = (int)n[l];
@@ -2986,6 +3056,9 @@ int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level) {
 }
 int amgb_hierarchy_matrix_free(const amgb_hierarchy* h, int level) {
   return (h && h->leg_ok(level) && h->legs[level].matrix_free) ? 1 : 0;
+}
+int amgb_hierarchy_dictionary_types(const amgb_hierarchy* h, int level) {
+  return (h && h->leg_ok(level)) ? h->legs[level].dict_types : 0;
 }
 int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info) {
   return guarded([&] {

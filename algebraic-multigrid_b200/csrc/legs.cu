@@ -53,8 +53,27 @@ bool act_mf(const Params& P, cudaStream_t s, int action, int* warps_per_sm) {
   return true;
 }
 
+template <int KIND, unsigned MASK, int NU, bool FAST>
+bool act_dict(const Params& P, cudaStream_t s, int action, int* warps_per_sm) {
+  auto kern = k_stream_leg_dict<KIND, MASK, NU, FAST>;
+  if (action == 1) {
+    kern<<<(P.n_warps + 3) / 4, 128, 0, s>>>(P);
+    check(cudaGetLastError(), "k_stream_leg_dict launch");
+  } else if (action == 2) {
+    cudaFuncAttributes fa{};
+    check(cudaFuncGetAttributes(&fa, kern), "cudaFuncGetAttributes(k_stream_leg_dict)");
+    if (warps_per_sm) *warps_per_sm = std::max(1, 65536 / (std::max(fa.numRegs, 1) * 128)) * 4;
+  }
+  return true;
+}
+
 template <int KIND, unsigned MASK, bool FAST>
 bool by_nu(const Params& P, cudaStream_t s, int action, int* wps) {
+  if (P.dict_types > 0) {
+    if (P.nu == 1) return act_dict<KIND, MASK, 1, FAST>(P, s, action, wps);
+    if (P.nu == 2) return act_dict<KIND, MASK, 2, FAST>(P, s, action, wps);
+    return false;
+  }
   if constexpr (MASK == kMask5) {
     if (P.matrix_free) {
       const int pf = env_int("AMGB_SLEG_MF_PF", 4);

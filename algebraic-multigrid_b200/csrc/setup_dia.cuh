@@ -146,5 +146,67 @@ __global__ void __launch_bounds__(256) k_check_const5(const double* __restrict__
   }
 }
 
+// ---- row-type dictionary: the distinct rows of a DIA operator (the Galerkin levels of a constant
+// stencil have a few dozen), found with a small open-addressing hash table of 64-bit row hashes.
+// Every row is afterwards compared bit for bit with its table row (k_dict_assign), so a hash
+// collision can only make the build fail, never produce a wrong operator.
+constexpr int kDictSlots = 4096;
+__device__ __forceinline__ unsigned long long dict_row_hash(const double* __restrict__ val, int ld, int nd, int t) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (int d = 0; d < nd; ++d) {
+    h ^= (unsigned long long)__double_as_longlong(val[(size_t)d * ld + t]);
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+  }
+  return h ? h : 1ull;  // 0 marks an empty slot
+}
+// slot of hash h (inserting it when insert is set); -1: table full
+__device__ __forceinline__ int dict_find(unsigned long long* keys, unsigned long long h, bool insert) {
+  int slot = (int)(h % kDictSlots);
+  for (int probes = 0; probes < kDictSlots; ++probes) {
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(keys + slot);
+    if (cur == h) return slot;
+    if (cur == 0ull) {
+      if (!insert) return -1;
+      const unsigned long long old = atomicCAS(keys + slot, 0ull, h);
+      if (old == 0ull || old == h) return slot;
+    }
+    slot = (slot + 1 == kDictSlots) ? 0 : slot + 1;
+  }
+  return -1;
+}
+__global__ void __launch_bounds__(256) k_dict_insert(const double* __restrict__ val, int n, int ld, int nd,
+                                                     unsigned long long* keys, int* rep, int* overflow) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int slot = dict_find(keys, dict_row_hash(val, ld, nd, t), true);
+  if (slot < 0) {
+    *overflow = 1;
+    return;
+  }
+  if (*reinterpret_cast<volatile int*>(rep + slot) > t) atomicMin(rep + slot, t);  // representative = first row
+}
+__global__ void __launch_bounds__(256) k_dict_table(const double* __restrict__ val, int ld, int nd, const int* rep_of_id,
+                                                    int n_types, double* table) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_types * nd) return;
+  table[i] = val[(size_t)(i % nd) * ld + rep_of_id[i / nd]];
+}
+__global__ void __launch_bounds__(256) k_dict_assign(const double* __restrict__ val, int n, int ld, int nd,
+                                                     unsigned long long* keys, const short* slot_id,
+                                                     const double* __restrict__ table, unsigned char* tid, int* bad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int slot = dict_find(keys, dict_row_hash(val, ld, nd, t), false);
+  const int id = slot >= 0 ? (int)slot_id[slot] : -1;
+  if (id < 0) {
+    *bad = 1;
+    return;
+  }
+  for (int d = 0; d < nd; ++d)
+    if (__double_as_longlong(val[(size_t)d * ld + t]) != __double_as_longlong(table[id * nd + d])) *bad = 1;
+  tid[t] = (unsigned char)id;
+}
+
 }  // namespace setup
 }  // namespace amgb

@@ -58,8 +58,11 @@ __device__ __forceinline__ double rcp_refined(double d) {
 }
 
 // MF: matrix-free five-point operator (Params::cst, presence of a neighbour decided from the row index)
-template <int KIND, unsigned MASK, int NU, int PF_, bool FAST, bool MF = false>
+// DICT: the operator row comes from a table of the level's distinct rows in shared memory, selected
+//       by one byte per row (Params::tid / table) -- 1 instead of 8 x diagonals bytes per row from HBM
+template <int KIND, unsigned MASK, int NU, int PF_, bool FAST, bool MF = false, bool DICT = false>
 struct Leg {
+  static_assert(!(MF && DICT), "one operator source");
   static_assert(!MF || MASK == kMask5, "the matrix-free variant is the five-point stencil");
   static constexpr int ND = popc9(MASK);
   static constexpr int NS = stages(KIND, NU);                // chained stencil stages
@@ -78,6 +81,7 @@ struct Leg {
   // first / last of its grid line -- (k + base) mod m, the same for every row a lane visits
   struct Lane {
     double a_left, a_right, w;  // w = omega / diag (fast arithmetic)
+    const double* table;        // DICT: the row table in shared memory
   };
   // operator row of global row kg, entries in ascending column order: -m, -1, 0, +1, +m
   static __device__ __forceinline__ void mf_row(const Params& P, const Lane& Z, int kg, double (&a)[5]) {
@@ -113,9 +117,13 @@ struct Leg {
   }
 
   // loads of the line whose row on this lane is k (clamped to the rows that exist)
-  static __device__ __forceinline__ void load(Line& L, const Params& P, int k) {
+  static __device__ __forceinline__ void load(Line& L, const Params& P, int k, const double* table = nullptr) {
     const int kc = min(max(k, P.row_lo), P.row_hi1);
-    if constexpr (!MF) {
+    if constexpr (DICT) {
+      const double* row = table + (int)__ldg(P.tid + kc) * ND;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) L.a[d] = row[d];
+    } else if constexpr (!MF) {
 #pragma unroll
       for (int d = 0; d < ND; ++d) L.a[d] = __ldg(P.vd[d] + kc);
     }
@@ -135,7 +143,7 @@ struct Leg {
   // no registers, the later LDG then hits L2 (lower latency = fewer lines needed in flight)
   static __device__ __forceinline__ void prefetch(const Params& P, int k) {
     const int kc = min(max(k, P.row_lo), P.row_hi1);
-    if constexpr (!MF) {
+    if constexpr (!MF && !DICT) {
 #pragma unroll
       for (int d = 0; d < ND; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.vd[d] + kc));
     }
@@ -238,7 +246,7 @@ struct Leg {
   template <int P_>
   static __device__ __forceinline__ void step(State& S, const Params& P, int k1, const Own& own, const Lane& Z) {
     const int m = P.m;
-    load(S.R[(P_ + PF) % RS], P, k1 + PF * m);
+    load(S.R[(P_ + PF) % RS], P, k1 + PF * m, Z.table);
     if (P.l2_ahead > 0) prefetch(P, k1 + (PF + P.l2_ahead) * m);
     // ---- input stage, line jj + 1
     {
@@ -386,8 +394,12 @@ struct Leg {
     return __any_sync(0xffffffffu, wrote);
   }
 
-  static __device__ __forceinline__ void run(const Params& P) {
+  static __device__ __forceinline__ void run(const Params& P, double* smem_table = nullptr) {
     const int lane = threadIdx.x & 31;
+    if constexpr (DICT) {  // every block keeps its own copy of the row table
+      for (int i = threadIdx.x; i < P.dict_types * ND; i += blockDim.x) smem_table[i] = __ldg(P.table + i);
+      __syncthreads();
+    }
     // warps past the end redo the last tile without storing anything: no thread-dependent
     // branch ahead of the shuffles
     const int warp_raw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -414,6 +426,7 @@ struct Leg {
     const int jA = j0 - NS;
     int k1 = jA * P.m + (i0 - H) + lane;  // this lane's row on line jA
     Lane Z{};
+    Z.table = smem_table;
     if constexpr (MF) {
       int pos = (i0 - H + lane + P.base) % P.m;  // position of this lane's rows in their grid line
       if (pos < 0) pos += P.m;
@@ -434,7 +447,7 @@ struct Leg {
       if (__any_sync(0xffffffffu, wait_at == left)) wait_side(P.sync, 1, edge_hi);
     }
 #pragma unroll
-    for (int q = 0; q < PF; ++q) load(S.R[q], P, k1 + q * P.m);
+    for (int q = 0; q < PF; ++q) load(S.R[q], P, k1 + q * P.m, Z.table);
     const int first = left;
     while (left > 0) {
       // (a vote, so the compiler knows the branch is warp-uniform and keeps the shuffles below convergent)
@@ -456,6 +469,12 @@ template <int KIND, unsigned MASK, int NU, int PF_, bool FAST>
 __global__ void __launch_bounds__(128, (popc9(MASK) <= 5 && PF_ == 2) ? 4 : 3)
     k_stream_leg(const __grid_constant__ Params P) {
   Leg<KIND, MASK, NU, PF_, FAST>::run(P);
+}
+// row-type dictionary legs (at most 256 distinct operator rows on the level)
+template <int KIND, unsigned MASK, int NU, bool FAST>
+__global__ void __launch_bounds__(128, (popc9(MASK) <= 5) ? 4 : 3) k_stream_leg_dict(const __grid_constant__ Params P) {
+  __shared__ double table[256 * popc9(MASK)];
+  Leg<KIND, MASK, NU, 2, FAST, false, true>::run(P, table);
 }
 // matrix-free five-point legs: no operator row in the register ring, so more lines in flight and more
 // resident warps

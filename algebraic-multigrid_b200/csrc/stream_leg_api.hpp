@@ -81,6 +81,11 @@ struct Params {
   // 0, +1, +m wherever the neighbour exists and empty elsewhere): no operator row is loaded
   int matrix_free;
   double cst[5];
+  // row-type dictionary variant (the operator has at most 256 distinct rows, VERIFIED at setup): one
+  // byte per row selects a row of the table, which every block copies into shared memory
+  int dict_types;              // 0: off
+  const unsigned char* tid;    // type of every row of the window
+  const double* table;         // dict_types x (number of diagonals)
   double omega;
   const double* val;
   const double* vd[9];  // val + d * ld

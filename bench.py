@@ -421,8 +421,14 @@ def run_b200(a):
     per_kernel = {}
 
     def mat_bytes(l):
-        """operator bytes a leg of level l streams: none when the level runs matrix-free"""
-        return 0 if mg.matrix_free(l) else mg.matrix_bytes(l)
+        """operator bytes a leg of level l streams on this rank: none when the level runs matrix-free,
+        one byte per row when it runs from a row-type dictionary, else the stored DIA / SELL bytes"""
+        if mg.matrix_free(l):
+            return 0
+        if mg.dictionary_types(l):
+            a0, a1 = mg.local_range(l)
+            return a1 - a0
+        return mg.matrix_bytes(l)
 
     legs_timed = []
     if fused0:
@@ -439,7 +445,7 @@ def run_b200(a):
                 alg = mat_bytes(l) + ((24 if (l == 0 or kind == 5) else 16) * rows) + 8 * (rows // 2)
                 legs_timed.append({"level": l, "leg": nm, "ms": t_ms, "algorithmic_bytes": alg,
                                    "GB/s": alg / (t_ms * 1e-3) / 1e9, "frac": alg / (t_ms * 1e-3) / 1e9 / peak,
-                                   "matrix_free": bool(mg.matrix_free(l))})
+                                   "matrix_free": bool(mg.matrix_free(l)), "dictionary_types": mg.dictionary_types(l)})
         top = max(legs_timed, key=lambda x: x["ms"])
         kern_ms, bytes0 = top["ms"], top["algorithmic_bytes"]
         plan = mg.leg_plan(top["level"], up=(top["leg"] == "up"))
@@ -450,7 +456,9 @@ def run_b200(a):
             "%d Jacobi sweeps + residual + restriction in one pass" % smoother.n_iters if top["leg"] == "down"
             else "prolongation + add + %d Jacobi sweeps in one pass" % smoother.n_iters,
             "fast" if arith == amg.ARITH_FAST else "reference-order",
-            "matrix-free five-point stencil" if top["matrix_free"] else mg.format(top["level"]) + " layout")
+            "matrix-free five-point stencil" if top["matrix_free"] else
+            "row-type dictionary, %d types" % top["dictionary_types"] if top["dictionary_types"] else
+            mg.format(top["level"]) + " layout")
     else:
         kern_ms = mg.time_kernel(0, 0, warmup=3, reps=20)
         bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0)       # this rank's row block
@@ -554,6 +562,7 @@ def run_b200(a):
                    "rss_after_timed_cycles": rss_after,
                    "fused_legs": [bool(mg.fused_legs(l)) for l in range(levels - 1)], "tail_first": mg.tail_first(),
                    "matrix_free_levels": [l for l in range(levels - 1) if mg.matrix_free(l)],
+                   "dictionary_types": [mg.dictionary_types(l) for l in range(levels - 1)],
                    "mid_levels": list(mg.mid_range()),
                    "launches_per_vcycle": mg.launches_per_vcycle(),
                    "vcycle_layout_bytes": layout_bytes,

@@ -172,8 +172,13 @@ typedef struct amgb_options {
                                the device) to be a constant five-point stencil runs
                                matrix-free legs: the coefficients travel as kernel
                                parameters and no operator row is read (28 instead of 68
-                               bytes per row).  The arithmetic, hence
-                               every bit of the result, is unchanged                      */
+                               bytes per row); bit 7 (default on): a
+                               level whose operator has at most 256 DISTINCT rows (the
+                               Galerkin levels of a constant stencil have a few dozen) runs
+                               dictionary legs: one byte per row selects a row of a table
+                               held in shared memory, every row verified against it at
+                               setup (1 instead of 8 x diagonals operator bytes per row).
+                               The arithmetic, hence every bit of the result, is unchanged */
   int arith;                /* arithmetic of the damped-Jacobi cycle's kernels.
                                AMGB_ARITH_REFERENCE (default): the oracle's operation order,
                                separate multiply / subtract, IEEE division -- bit-identical
@@ -314,6 +319,9 @@ int amgb_coarse_solve(amgb_hierarchy* h);
 int amgb_hierarchy_fused_legs(const amgb_hierarchy* h, int level);
 /* 1 when the level's fused legs run matrix-free (option fuse bit 6, operator verified at setup) */
 int amgb_hierarchy_matrix_free(const amgb_hierarchy* h, int level);
+/* number of distinct operator rows when the level's fused legs run from a row-type dictionary
+ * (option fuse bit 7), else 0 */
+int amgb_hierarchy_dictionary_types(const amgb_hierarchy* h, int level);
 /* first level of the coarse tail that runs in one launch (option fuse bit 4), -1 if none */
 int amgb_hierarchy_tail_first(const amgb_hierarchy* h);
 int amgb_hierarchy_leg_plan(const amgb_hierarchy* h, int level, int up, int64_t* info);

@@ -777,3 +777,37 @@ def test_matrix_free_needs_an_exactly_constant_stencil():
     for _ in range(2):
         mg.vcycle(); mo.vcycle()
     assert rel(mg.get_soln(0), mo.u(0)) <= RTOL
+
+
+# ----------------------------------------------------------------- row-type dictionary legs (fuse bit 7)
+@pytest.mark.parametrize("n,L,eps,nu", [(100, 9, 1.0, 2), (129, 10, 1e-3, 2), (257, 13, 1.0, 1), (513, 14, 1.0, 2),
+                                        (1025, 14, 1.0, 2)])
+def test_dictionary_legs_are_bit_identical(n, L, eps, nu):
+    """The fused legs read one byte per row and take the operator row from a table of the level's
+    distinct rows (verified at setup); every level's iterate and right-hand side stay bit-identical."""
+    sm = amg.DampedJacobi(2.0 / 3.0, nu)
+    dic, mo, _ = make_pair(n, L, sm, eps, fuse=1 | 4 | 128)
+    assert dic.fused_legs(0) and 1 <= dic.dictionary_types(0) <= 256 and not dic.matrix_free(0)
+    assert sum(dic.dictionary_types(l) > 0 for l in range(L - 1)) >= 2
+    for _ in range(3):
+        dic.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert dic.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert dic.get_rhs(l).tobytes() == mo.f(l).tobytes(), l
+
+
+def test_dictionary_needs_few_distinct_rows():
+    """A level-0 operator with more than 256 distinct rows keeps the plain DIA legs."""
+    n, L = 129, 10
+    A, b, _ = problem(n)
+    rng = np.random.default_rng(4)
+    diag = np.flatnonzero(A.rowidx == np.repeat(np.arange(n * n), np.diff(A.colptr)))
+    A.val[diag] *= 1.0 + 1e-3 * rng.random(n * n)            # every diagonal entry different
+    sm = amg.DampedJacobi(2.0 / 3.0, 2)
+    mg = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1, fuse=1 | 4 | 64 | 128)
+    assert mg.fused_legs(0) and mg.dictionary_types(0) == 0 and not mg.matrix_free(0)
+    mo = O.Multigrid(O.Csc.from_arrays(A.rows, A.cols, A.colptr, A.rowidx, A.val), b, L, 1e-9, 1, 1,
+                     O.SMOOTHER_JACOBI, 2, 2.0 / 3.0)
+    for _ in range(2):
+        mg.vcycle(); mo.vcycle()
+    assert mg.get_soln(0).tobytes() == mo.u(0).tobytes()
