@@ -275,6 +275,7 @@ struct Operator {
     MT = transpose(M);
     symmetric = bitwise_equal(M, MT);
     block = true;
+    block_row0 = row_begin;
     n = n_own;
     n_mat = rows_stored;
     Dia D = build_dia_block(host_rows_of_A(), row_begin, rows_stored);
@@ -460,11 +461,15 @@ struct Operator {
     LAUNCH(kern, 1, lines_T + 32, lines_smem, s, L, g, u);  // + the producer warp
   }
 
+  // first owned global row of a row block (0 for a whole level); the colour mirrors list GLOBAL rows
+  int block_row0 = 0;
   void ensure_colors(cudaStream_t s) {
     if (have_colors) return;
+    // the colouring is that of the WHOLE operator (every rank holds the host matrix), so a sharded
+    // sweep visits the rows in the same colour order as one GPU does: same bits
     n_colors = greedy_coloring(M, MT, color);
     std::vector<std::vector<int>> members(n_colors);
-    for (int k = 0; k < n; ++k) members[color[k]].push_back(k);
+    for (int k = block_row0; k < block_row0 + n; ++k) members[color[k]].push_back(k);
     color_sell.clear();
     for (int c = 0; c < n_colors; ++c) {
       color_sell.emplace_back(new DevMat());
@@ -597,10 +602,14 @@ void options_default(amgb_options* o) {
   o->gs_mode = AMGB_GS_AUTO;
   o->use_graph = 1;
   o->skip_dead_coarse_smooth = 1;
-  // zero-guess sweep, streaming legs, coarse tail, mid levels, matrix-free five-point legs, row-type
-  // dictionary legs;
-  // prolongation fusion (bit 1) measured slower
-  o->fuse = 1 | 4 | 16 | 32 | 64 | 128;
+  // zero-guess sweep, streaming legs, coarse tail, mid levels; prolongation fusion (bit 1) measured
+  // slower.  The compressed operator formats (bit 6 matrix-free five-point legs, bit 7 row-type
+  // dictionary legs) are opt-in: they apply to operators with verified structure only and turn the
+  // legs from HBM-bound into issue-bound kernels (faster, but no longer a bandwidth roofline story);
+  // AMGB_COMPRESS=1 switches them on for hierarchies created with the default options.
+  o->fuse = 1 | 4 | 16 | 32;
+  if (const char* c = std::getenv("AMGB_COMPRESS"))
+    if (std::string(c) == "1") o->fuse |= 64 | 128;
   o->arith = AMGB_ARITH_REFERENCE;
 }
 
@@ -947,8 +956,9 @@ struct amgb_hierarchy {
 
   void prepare_smoother(int l) {
     if (lv[l].sharded) {
-      if (opt.smoother != AMGB_SMOOTHER_JACOBI)
-        throw std::invalid_argument("sharded levels support the damped-Jacobi smoother only");
+      if (opt.smoother == AMGB_SMOOTHER_GS)
+        throw std::invalid_argument("lexicographic Gauss-Seidel cannot run on a sharded level");
+      if (opt.smoother == AMGB_SMOOTHER_COLOR_GS) ops[l]->ensure_colors(stream);
       return;
     }
     if (opt.smoother == AMGB_SMOOTHER_GS) {
@@ -971,8 +981,9 @@ struct amgb_hierarchy {
     ++halo_exchanges_per_vcycle;
     if (p2p) {
       const int v = (base == S.u.p) ? 0 : (base == S.tmp.p ? 1 : 2);
-      const int site = site_cursor++;
-      if (site >= kMaxSites) throw ApiError(AMGB_ESTATE, "too many halo-exchange sites");
+      // flags and epochs are per site, epochs only ever grow: a site may be reused (every rank makes the
+      // same sequence of exchanges, so they all wrap at the same call)
+      const int site = site_cursor++ % kMaxSites;
       dev::HaloSide lo{}, hi{};
       if (g > 0) {  // my first rows -> rank g-1's upper halo
         lo.peer_dst = peers[l].lo[v] + peers[l].lo_halo_lo + peers[l].lo_n_own;
@@ -1057,9 +1068,20 @@ struct amgb_hierarchy {
           A.gs_direction(false, S.f.p, S.u.p, S.tmp.p, opt.gs_mode, s);
         }
       } else if (opt.smoother == AMGB_SMOOTHER_COLOR_GS) {
+        // Row-block sharded level: the colour mirrors list global rows, so the vectors are handed over
+        // shifted to global numbering; one halo exchange before every colour pass (a pass reads the
+        // other colours' latest values, some of which live on ranks +-1).
+        double* u_g = S.sharded ? S.u.p - (S.s - S.halo_lo) : S.u.p;
+        const double* f_g = S.sharded ? S.f.p - S.s : S.f.p;
         for (int64_t it = 0; it < iters; ++it) {
-          for (int c = 0; c < A.n_colors; ++c) A.color_pass(c, S.f.p, S.u.p, s);
-          for (int c = A.n_colors - 1; c >= 0; --c) A.color_pass(c, S.f.p, S.u.p, s);
+          for (int c = 0; c < A.n_colors; ++c) {
+            exchange(l, S.u.p, s);
+            A.color_pass(c, f_g, u_g, s);
+          }
+          for (int c = A.n_colors - 1; c >= 0; --c) {
+            exchange(l, S.u.p, s);
+            A.color_pass(c, f_g, u_g, s);
+          }
         }
       }
       return;
@@ -2494,14 +2516,14 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
   // ---- partition (sharded runs only) ----
   const int world = comm ? comm->world : 1;
   if (world > 1) {
-    if (o.smoother != AMGB_SMOOTHER_JACOBI)
-      throw std::invalid_argument("the row-block sharded V-cycle supports the damped-Jacobi smoother only "
-                                  "(lexicographic Gauss-Seidel is a single-GPU path)");
+    if (o.smoother == AMGB_SMOOTHER_GS)
+      throw std::invalid_argument("the row-block sharded V-cycle supports the damped-Jacobi and multicolour "
+                                  "Gauss-Seidel smoothers (lexicographic Gauss-Seidel is a single-GPU path)");
     // With the fused legs on, only levels whose operator is a 3 x 3 line stencil are worth
     // sharding (they run as streaming legs on the rank's window); the levels below, a few
     // hundred thousand rows at most, are agglomerated.
     int max_sharded = 1 << 30;
-    if ((o.fuse & 4) && (o.smoother_iters == 1 || o.smoother_iters == 2)) {
+    if ((o.fuse & 4) && o.smoother == AMGB_SMOOTHER_JACOBI && (o.smoother_iters == 1 || o.smoother_iters == 2)) {
       max_sharded = 0;
       for (int l = 0; l + 1 < L; ++l) {
         const std::vector<int>& offs = level_off[l];

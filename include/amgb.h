@@ -167,13 +167,14 @@ typedef struct amgb_options {
                                (default on): the mid levels between the streamed ones and
                                that tail run all their down legs in one launch and all
                                their up legs in another (shared-memory tiles with
-                               recomputed halos, mid_levels.cuh); bit 6 (default on): a
-                               level whose operator is VERIFIED at setup (bit for bit, on
+                               recomputed halos, mid_levels.cuh); bit 6 (opt-in, or
+                               AMGB_COMPRESS=1): a level whose operator is VERIFIED at setup (bit for bit, on
                                the device) to be a constant five-point stencil runs
                                matrix-free legs: the coefficients travel as kernel
                                parameters and no operator row is read (28 instead of 68
-                               bytes per row); bit 7 (default on): a
-                               level whose operator has at most 256 DISTINCT rows (the
+                               bytes per row); bit 7 (opt-in, or
+                               AMGB_COMPRESS=1): a level whose operator has at most 256
+                               DISTINCT rows (the
                                Galerkin levels of a constant stencil have a few dozen) runs
                                dictionary legs: one byte per row selects a row of a table
                                held in shared memory, every row verified against it at
@@ -208,8 +209,10 @@ int amgb_hierarchy_destroy(amgb_hierarchy* h);
  * residual / prolongation; coarser levels are agglomerated: their right-hand side is
  * gathered once per cycle and every rank keeps a replica (instead of GPU 0 solving
  * and scattering back, which would add a second collective).  Every rank passes the
- * same full A and b; vectors are given / returned at full length.  Damped Jacobi only
- * (lexicographic Gauss-Seidel is a single-GPU path).
+ * same full A and b; vectors are given / returned at full length (or per row block, the *_local
+ * entry points).  Damped Jacobi (fused legs that push their halos themselves) and multicolour
+ * Gauss-Seidel (one halo exchange per colour pass) are the partitioned smoothers; lexicographic
+ * Gauss-Seidel is a single-GPU path.
  * ---------------------------------------------------------------------- */
 typedef struct amgb_comm amgb_comm;
 int amgb_comm_unique_id_bytes(void);

@@ -32,8 +32,11 @@ def main():
     amg.lib().amgb_set_device(local)
     dist.init_process_group("gloo")
     comm = amg.Comm(rank, world, id_exchanger(rank))
-    # (n, levels, eps, min rows per rank, Jacobi sweeps, fuse option or None = default, arithmetic)
+    # (n, levels, eps, min rows per rank, sweeps (negative: multicolour Gauss-Seidel with that many
+    #  symmetric sweeps), fuse option or None = default, arithmetic)
     cases = [(257, 10, 1.0, 1 << 10, 2, None, amg.ARITH_REFERENCE),
+             (257, 10, 1.0, 1 << 10, -1, None, amg.ARITH_REFERENCE),    # multicolour GS: one exchange per colour pass
+             (129, 9, 1e-3, 900, -2, None, amg.ARITH_REFERENCE),
              (513, 12, 1e-3, 1 << 12, 2, None, amg.ARITH_REFERENCE),
              (513, 12, 1.0, 1 << 12, 2, None, amg.ARITH_FAST),
              (257, 10, 1.0, 1 << 10, 1, None, amg.ARITH_REFERENCE),     # one sweep per smooth call
@@ -46,13 +49,15 @@ def main():
     fused_push = want_mode == "peer" and os.environ.get("AMGB_FUSED_PUSH", "1") != "0"
     for n, L, eps, min_rows, nu, fuse, arith in cases:
         A, b = amg.Grid.laplacian(n, eps), amg.Grid.rhs(n)
-        sm = amg.DampedJacobi(2.0 / 3.0, nu)
+        color = nu < 0
+        nu = abs(nu)
+        sm = amg.MulticolorGaussSeidel(nu) if color else amg.DampedJacobi(2.0 / 3.0, nu)
         for use_graph in (False, True):
             mg = amg.Multigrid(None, sm, A, b, L, 1e-9, 1, 1, comm=comm, min_rows_per_rank=min_rows,
                                use_graph=use_graph, fuse=fuse, arith=arith)
             ns = mg.n_sharded_levels()
             assert ns >= 1, ns
-            legs = fuse is None and nu in (1, 2)
+            legs = fuse is None and nu in (1, 2) and not color
             if legs:  # the sharded levels run as fused legs on the rank's window (block + ghost rows)
                 assert all(mg.fused_legs(l) for l in range(ns)), [mg.fused_legs(l) for l in range(L - 1)]
             assert mg.halo_mode() == want_mode, (mg.halo_mode(), want_mode)
@@ -85,7 +90,8 @@ def main():
             assert mg.get_rhs_local(0).tobytes() == f_new[b0:b1].tobytes()
             mg.set_soln(0, np.zeros(n * n)); mg.set_rhs(0, b)
             if rank == 0 and n <= 600 and not use_graph and arith == amg.ARITH_REFERENCE:
-                mo = O.Multigrid(O.laplacian(n, eps), b, L, 1e-9, 1, 1, O.SMOOTHER_JACOBI, nu, 2.0 / 3.0)
+                mo = O.Multigrid(O.laplacian(n, eps), b, L, 1e-9, 1, 1,
+                                 O.SMOOTHER_COLOR_GS if color else O.SMOOTHER_JACOBI, nu, 2.0 / 3.0)
                 for _ in range(3):
                     mo.vcycle()
                     mg.vcycle()
@@ -95,8 +101,9 @@ def main():
                     mg.vcycle()
                 mg.get_soln(0)  # collective: every rank takes part
             if rank == 0:
-                print("ok n=%d levels=%d sharded_levels=%d nu=%d fuse=%s arith=%d graph=%s halo=%s exchanges/vcycle=%d rss=%.6e" % (
-                    n, L, ns, nu, fuse, arith, use_graph, mg.halo_mode(), mg.halo_exchanges_per_vcycle(), r_sh), flush=True)
+                print("ok %s n=%d levels=%d sharded_levels=%d nu=%d fuse=%s arith=%d graph=%s halo=%s exchanges/vcycle=%d rss=%.6e" % (
+                    "color" if color else "jacobi", n, L, ns, nu, fuse, arith, use_graph, mg.halo_mode(),
+                    mg.halo_exchanges_per_vcycle(), r_sh), flush=True)
             del mg, single
     dist.barrier()
     del comm
