@@ -2594,7 +2594,7 @@ static void create_hierarchy(amgb_comm* comm, int64_t min_rows_per_rank, int n_r
     S.u.zero(s);
     S.f.alloc(S.n_mat + 8);
     S.f.zero(s);
-    if (o.smoother == AMGB_SMOOTHER_JACOBI) {
+    if (o.smoother == AMGB_SMOOTHER_JACOBI || S.sharded) {  // (sharded: every level vector is exported to the neighbours)
       S.tmp.alloc(S.n_vec() + 8);
       S.tmp.zero(s);
     }
