@@ -448,11 +448,16 @@ struct Leg {
     }
 #pragma unroll
     for (int q = 0; q < PF; ++q) load(S.R[q], P, k1 + q * P.m, Z.table);
-    const int first = left;
-    while (left > 0) {
-      // (a vote, so the compiler knows the branch is warp-uniform and keeps the shuffles below convergent)
-      if (waits && __any_sync(0xffffffffu, left == wait_at && left != first)) wait_side(P.sync, 1, edge_hi);
-      steps<0>(S, P, k1, left, own, Z);
+    if (!waits) {
+      // single GPU: the plain line loop (its own copy, so the multi-GPU bookkeeping below costs it nothing)
+      while (left > 0) steps<0>(S, P, k1, left, own, Z);
+    } else {
+      const int first = left;
+      while (left > 0) {
+        // (a vote, so the compiler knows the branch is warp-uniform and keeps the shuffles below convergent)
+        if (__any_sync(0xffffffffu, left == wait_at && left != first)) wait_side(P.sync, 1, edge_hi);
+        steps<0>(S, P, k1, left, own, Z);
+      }
     }
 
     if (edge_lo || edge_hi) {
