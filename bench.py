@@ -639,8 +639,11 @@ def run_micro(a, amg, rank, world, local, dist, comm, json_fd):
     ms_j = max_over_ranks(mg.time_kernel(0, 9, warmup=n_warm, reps=a.steps))     # CUDA events around `steps` launches
     barrier()
     tw1 = time.time()
-    clocks = sampler.stop(tw0, tw1) if sampler else None
     ms_r = max_over_ranks(mg.time_kernel(0, 11, warmup=n_warm, reps=a.steps))
+    barrier()
+    # (the sampler is stopped only now: stopping it takes rank 0 up to a second, and a rank that enters
+    # the next collective timing loop late shows up in every other rank's first launches)
+    clocks = sampler.stop(tw0, tw1) if sampler else None
     launches = amg.kernel_launches() - launches0
     B0 = 12 * nnz + 28 * N + 4                          # CSR-equivalent bytes per pass
     dia_rank = mg.matrix_bytes(0) + 24 * (r1 - r0)      # what this rank's DIA kernels stream per pass
