@@ -930,12 +930,15 @@ struct amgb_hierarchy {
         }
       }
       // edge chunks: those that read ghost rows (within NS + 2 lines of the block edge) or produce pushed rows
-      const int64_t rows_per_chunk = (int64_t)P.LJ * P.m;
       const int64_t lo_bound = (int64_t)lo_reach + (int64_t)(NS + 2) * P.m;
       const int64_t hi_bound = (int64_t)hi_reach - (int64_t)(NS + 2) * P.m;
-      Y.edge_lo_chunks = (int)std::min<int64_t>(P.n_chunks, (lo_bound + rows_per_chunk - 1) / rows_per_chunk);
+      Y.edge_lo_chunks = 0;  // chunks whose first row lies below lo_bound
+      while (Y.edge_lo_chunks < P.n_chunks && (int64_t)P.chunk_begin(Y.edge_lo_chunks) * P.m < lo_bound) ++Y.edge_lo_chunks;
       Y.edge_lo_chunks = std::max(Y.edge_lo_chunks, 1);
-      Y.edge_hi_chunk0 = hi_bound <= 0 ? 0 : (int)std::min<int64_t>(P.n_chunks - 1, hi_bound / rows_per_chunk);
+      Y.edge_hi_chunk0 = P.n_chunks - 1;  // first chunk whose last row lies above hi_bound
+      while (Y.edge_hi_chunk0 > 0 &&
+             (int64_t)(P.chunk_begin(Y.edge_hi_chunk0 - 1) + P.chunk_lines(Y.edge_hi_chunk0 - 1)) * P.m > hi_bound)
+        --Y.edge_hi_chunk0;
       Y.expected[0] = Y.edge_lo_chunks * P.n_strips;
       Y.expected[1] = (P.n_chunks - Y.edge_hi_chunk0) * P.n_strips;
     };
@@ -1390,9 +1393,7 @@ struct amgb_hierarchy {
         P.Wu = 32 - 2 * (NS + X);
         P.n_strips = (P.m + P.Wu - 1) / P.Wu;
         const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / env_int("AMGB_SLEG_MINLINES", 8)));
-        P.LJ = (P.n_lines + chunks - 1) / chunks;
-        P.n_chunks = (P.n_lines + P.LJ - 1) / P.LJ;
-        P.n_warps = P.n_strips * P.n_chunks;
+        P.set_chunks(chunks, env_int("AMGB_SLEG_EDGE_HALF", 1) != 0);  // (only used with the fused halo push)
         P.ld = W.ld;
         P.n_coarse = (int)n[l + 1];
         P.omega = opt.omega;
@@ -1459,9 +1460,7 @@ struct amgb_hierarchy {
             P.Wu = 32 - 2 * (NS + X);
             P.n_strips = (P.m + P.Wu - 1) / P.Wu;
             const int chunks = std::max(1, std::min(warps_target / P.n_strips, P.n_lines / env_int("AMGB_SLEG_MINLINES", 8)));
-            P.LJ = (P.n_lines + chunks - 1) / chunks;
-            P.n_chunks = (P.n_lines + P.LJ - 1) / P.LJ;
-            P.n_warps = P.n_strips * P.n_chunks;
+            P.set_chunks(chunks, false);
             P.ld = A.dia.ld;
             P.n_coarse = (int)n[l + 1];
             P.omega = opt.omega;
@@ -1588,6 +1587,7 @@ struct amgb_hierarchy {
       CUDA_CHECK(cudaFuncSetAttribute(dev::k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tail_first = first;
   }
+  void launch_tail(cudaStream_t s) { LAUNCH(dev::k_coarse_tail, 1, 1024, tail_smem, s, tail); }
 
   // ---- mid levels (mid_levels.cuh): levels [mid_first, mid_end) of a damped-Jacobi cycle, all their
   // down legs in ONE launch and all their up legs in another (option fuse bit 5)
@@ -1726,7 +1726,7 @@ struct amgb_hierarchy {
       // it is stored in a private member without a getter and never read.
     }
     if (mid_first >= 0) mid_down(s);
-    if (lt < L) LAUNCH(dev::k_coarse_tail, 1, 1024, tail_smem, s, tail);
+    if (lt < L) launch_tail(s);
     else coarse_solve(s);
     if (mid_first >= 0) mid_up(s);
     if (n_sharded == 0) mark(3, s);
@@ -3315,7 +3315,7 @@ int amgb_time_kernel(amgb_hierarchy* h, int level, int kind, int warmup, int rep
       auto once = [&] {
         if (kind == 6) h->mid_down(s);
         else if (kind == 7) h->mid_up(s);
-        else if (h->tail_first > 0) LAUNCH(dev::k_coarse_tail, 1, 1024, h->tail_smem, s, h->tail);
+        else if (h->tail_first > 0) h->launch_tail(s);
         else h->coarse_solve(s);
       };
       for (int i = 0; i < warmup; ++i) once();

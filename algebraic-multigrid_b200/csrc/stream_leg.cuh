@@ -285,14 +285,16 @@ struct Leg {
   // RS consecutive steps (one period of the register ring); `left` counts the steps still to
   // do and is the same for every lane of the warp, so control flow stays convergent and the
   // shuffles need no re-convergence code.
-  template <int P_>
+  // VOTE: `left` differs from warp to warp (sharded levels: shorter edge chunks); the early exit then goes
+  // through a warp vote so that the compiler still knows the branch is warp-uniform
+  template <int P_, bool VOTE = false>
   static __device__ __forceinline__ void steps(State& S, const Params& P, int& k1, int& left, const Own& own, const Lane& Z) {
     if constexpr (P_ < RS) {
-      if (left <= 0) return;
+      if (VOTE ? !__any_sync(0xffffffffu, left > 0) : (left <= 0)) return;
       step<P_>(S, P, k1, own, Z);
       --left;
       k1 += P.m;
-      steps<P_ + 1>(S, P, k1, left, own, Z);
+      steps<P_ + 1, VOTE>(S, P, k1, left, own, Z);
     }
   }
 
@@ -301,13 +303,16 @@ struct Leg {
   // votes), so the shuffles of the line loop that follows need no re-convergence code: a warp
   // that is not at this edge polls its own epoch word, which equals the value waited for.
   static __device__ __forceinline__ void wait_side(const Sync& Y, int side, bool edge) {
-    const unsigned long long* epoch_word = Y.wait_epoch[side];
-    const unsigned long long* flag = (edge && Y.wait_flag[side] != nullptr) ? Y.wait_flag[side] : epoch_word;
-    const unsigned long long want = *epoch_word;
+    // only the edge warps load anything (predicated loads, no branch); the others fall straight through
+    edge = edge && Y.wait_flag[side] != nullptr;
+    const unsigned long long* flag = edge ? Y.wait_flag[side] : Y.wait_epoch[side];
+    unsigned long long want = 0ull;
+    if (edge) want = *Y.wait_epoch[side];
     const long long t0 = clock64();
     while (true) {
-      // relaxed polling (no fence per poll, nothing at all for the warps that are not at the edge) ...
-      const unsigned long long seen = *reinterpret_cast<const volatile unsigned long long*>(flag);
+      // relaxed polling (no fence per poll) ...
+      unsigned long long seen = ~0ull;
+      if (edge) seen = *reinterpret_cast<const volatile unsigned long long*>(flag);
       if (__all_sync(0xffffffffu, seen >= want)) break;
       if (__any_sync(0xffffffffu, clock64() - t0 > Y.timeout_cycles)) {  // a neighbour died or stalled
         *Y.timed_out = 1;
@@ -315,8 +320,8 @@ struct Leg {
       }
       __nanosleep(32);
     }
-    // ... and ONE acquire load once the flag is up, on the edge warps only: the neighbour's pushes
-    // (released system-wide before its flag store) are visible to the loads that follow
+    // ... and ONE acquire load once the flag is up: the neighbour's pushes (released system-wide before
+    // its flag store) are visible to the loads that follow
     if (edge) {
       unsigned long long seen;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
@@ -407,7 +412,8 @@ struct Leg {
     const int warp = dup ? P.n_warps - 1 : warp_raw;
     const int strip = warp % P.n_strips, chunk = warp / P.n_strips;
     const int i0 = strip * P.Wu, i1 = (i0 + P.Wu < P.m) ? i0 + P.Wu : P.m;
-    const int j0 = chunk * P.LJ, j1 = (j0 + P.LJ < P.n_lines) ? j0 + P.LJ : P.n_lines;
+    const int j0 = P.chunk_begin(chunk), n_mine = P.chunk_lines(chunk);
+    const int j1 = (j0 + n_mine < P.n_lines) ? j0 + n_mine : P.n_lines;
     Own own;
     {
       const int lo = max(j0 * P.m, P.own_begin), hi = min(j1 * P.m, P.own_end);
@@ -434,7 +440,9 @@ struct Leg {
       Z.a_right = (pos != P.m - 1) ? P.cst[3] : 0.0;
       Z.w = P.omega * rcp_refined(P.cst[2]);
     }
-    int left = P.LJ + 2 * NS;  // steps jA - 1 .. j0 + LJ + NS - 2 (a short last chunk just runs past its end)
+    // steps jA - 1 .. j0 + lines + NS - 2 (a short last chunk just runs past its end); on one GPU every
+    // chunk has LJ lines and the count is a kernel parameter, i.e. uniform for the compiler
+    int left = (waits ? n_mine : P.LJ) + 2 * NS;
     // The upper ghost rows are the LAST thing an upper-edge warp loads: its wait for the upper neighbour
     // is deferred to the last ring period before the loads reach them, so the neighbour's latency
     // hides behind the chunk's own work.  (Pushes into the neighbour happen after the wait either way.)
@@ -449,14 +457,16 @@ struct Leg {
 #pragma unroll
     for (int q = 0; q < PF; ++q) load(S.R[q], P, k1 + q * P.m, Z.table);
     if (!waits) {
-      // single GPU: the plain line loop (its own copy, so the multi-GPU bookkeeping below costs it nothing)
-      while (left > 0) steps<0>(S, P, k1, left, own, Z);
+      // single GPU: the plain line loop (its own copy, so the multi-GPU bookkeeping below costs it nothing);
+      // its trip count is a kernel parameter, i.e. provably uniform
+      int left_u = P.LJ + 2 * NS;
+      while (left_u > 0) steps<0>(S, P, k1, left_u, own, Z);
     } else {
       const int first = left;
-      while (left > 0) {
-        // (a vote, so the compiler knows the branch is warp-uniform and keeps the shuffles below convergent)
+      while (__any_sync(0xffffffffu, left > 0)) {
+        // (votes, so the compiler knows the branches are warp-uniform and keeps the shuffles convergent)
         if (__any_sync(0xffffffffu, left == wait_at && left != first)) wait_side(P.sync, 1, edge_hi);
-        steps<0>(S, P, k1, left, own, Z);
+        steps<0, true>(S, P, k1, left, own, Z);
       }
     }
 

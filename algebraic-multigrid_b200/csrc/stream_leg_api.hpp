@@ -69,6 +69,9 @@ struct Params {
   int Wu;        // owned elements per warp (32 - 2H)
   int n_strips;  // ceil(m / Wu)
   int LJ;        // lines per chunk
+  int LJ_edge;   // lines of the FIRST and the LAST chunk (= LJ on one GPU; half of it on a sharded level, so
+                 // that the warps which wait for / push to a neighbour have less streaming to do and the
+                 // flag latency hides behind the other chunks)
   int n_chunks;
   int n_warps;   // n_strips * n_chunks
   int ld;
@@ -96,6 +99,24 @@ struct Params {
   double* fc;
   Sync sync;
 
+  // first line and number of lines of chunk c
+  __host__ __device__ int chunk_begin(int c) const { return c == 0 ? 0 : LJ_edge + (c - 1) * LJ; }
+  __host__ __device__ int chunk_lines(int c) const { return (c == 0 || c == n_chunks - 1) ? LJ_edge : LJ; }
+  // chunk geometry for `chunks` chunks over n_lines lines; edge_half: the two edge chunks get half the lines
+  void set_chunks(int chunks, bool edge_half) {
+    if (chunks < 1) chunks = 1;
+    if (!edge_half || chunks < 4) {
+      LJ = (n_lines + chunks - 1) / chunks;
+      LJ_edge = LJ;
+      n_chunks = (n_lines + LJ - 1) / LJ;
+    } else {
+      LJ = (n_lines + chunks - 2) / (chunks - 1);  // two half chunks + (chunks - 2) whole ones
+      LJ_edge = (LJ + 1) / 2;
+      n_chunks = 2;
+      while (2 * LJ_edge + (n_chunks - 2) * LJ < n_lines) ++n_chunks;
+    }
+    n_warps = n_strips * n_chunks;
+  }
   // fills the derived fields; call after every other field is set
   void finish(int n_diag) {
     for (int d = 0; d < 9; ++d) vd[d] = val + (size_t)(d < n_diag ? d : 0) * (size_t)ld;
