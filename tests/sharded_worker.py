@@ -42,7 +42,8 @@ def main():
              (257, 10, 1.0, 1 << 10, 1, None, amg.ARITH_REFERENCE),     # one sweep per smooth call
              (257, 10, 1.0, 3000, 3, None, amg.ARITH_REFERENCE),        # odd count, per-operator kernels, uneven blocks
              (257, 10, 1.0, 1 << 10, 2, 0, amg.ARITH_REFERENCE),        # nothing fused: one exchange per sweep
-             (129, 9, 1.0, 700, 1, 0, amg.ARITH_REFERENCE)]
+             (129, 9, 1.0, 700, 1, 0, amg.ARITH_REFERENCE),
+             (513, 12, 1.0, 1 << 12, 2, 1 | 4 | 16 | 32 | 64 | 128, amg.ARITH_REFERENCE)]   # opt-in compressed operator formats
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         cases = [(2049, 15, 1.0, 1 << 16, 2, None, amg.ARITH_REFERENCE), (2049, 15, 1.0, 1 << 16, 2, None, amg.ARITH_FAST)]
     want_mode = os.environ.get("AMGB_HALO", "peer")
@@ -57,7 +58,7 @@ def main():
                                use_graph=use_graph, fuse=fuse, arith=arith)
             ns = mg.n_sharded_levels()
             assert ns >= 1, ns
-            legs = fuse is None and nu in (1, 2) and not color
+            legs = (fuse is None or fuse & 4) and nu in (1, 2) and not color
             if legs:  # the sharded levels run as fused legs on the rank's window (block + ghost rows)
                 assert all(mg.fused_legs(l) for l in range(ns)), [mg.fused_legs(l) for l in range(L - 1)]
             assert mg.halo_mode() == want_mode, (mg.halo_mode(), want_mode)
