@@ -137,6 +137,7 @@ SIGNATURES = {
     "amgb_hierarchy_vcycle_bytes": (_l, [_p]),
     "amgb_hierarchy_format": (_i, [_p, _i]),
     "amgb_hierarchy_matrix_bytes": (_l, [_p, _i]),
+    "amgb_hierarchy_n_diagonals": (_i, [_p, _i]),
     "amgb_time_kernel": (_i, [_p, _i, _i, _i, _i, C.POINTER(_d)]),
 }
 
@@ -682,6 +683,9 @@ class Multigrid:
 
     def matrix_bytes(self, level):
         return lib().amgb_hierarchy_matrix_bytes(self.h, level)
+
+    def n_diagonals(self, level):
+        return lib().amgb_hierarchy_n_diagonals(self.h, level)
 
     def pass_bytes(self, level):
         return lib().amgb_hierarchy_pass_bytes(self.h, level)

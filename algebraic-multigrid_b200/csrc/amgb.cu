@@ -3254,6 +3254,12 @@ int amgb_hierarchy_format(const amgb_hierarchy* h, int level) {
   if (!h || level < 0 || level >= h->L) return -1;
   return h->ops[level]->rows_of_A().is_dia ? AMGB_FORMAT_DIA : AMGB_FORMAT_SELL;
 }
+// diagonals of the level's DIA mirror (0 for SELL): what a fused leg streams is 8 x diagonals bytes per row
+int amgb_hierarchy_n_diagonals(const amgb_hierarchy* h, int level) {
+  if (!h || level < 0 || level >= h->L) return -1;
+  const DevMat& A = h->ops[level]->rows_of_A();
+  return A.is_dia ? A.dia.n_diag : 0;
+}
 int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level) {
   if (!h || level < 0 || level >= h->L) return -1;
   return h->ops[level]->rows_of_A().stored_bytes();

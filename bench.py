@@ -435,9 +435,11 @@ def run_b200(a):
         one byte per row when it runs from a row-type dictionary, else the stored DIA / SELL bytes"""
         if mg.matrix_free(l):
             return 0
+        a0, a1 = mg.local_range(l)
         if mg.dictionary_types(l):
-            a0, a1 = mg.local_range(l)
             return a1 - a0
+        if mg.fused_legs(l) and mg.n_diagonals(l) > 0:
+            return 8 * mg.n_diagonals(l) * (a1 - a0)    # a leg streams every diagonal of its rows
         return mg.matrix_bytes(l)
 
     legs_timed = []

@@ -353,6 +353,9 @@ int64_t amgb_hierarchy_launches_per_vcycle(const amgb_hierarchy* h);
 #define AMGB_FORMAT_DIA 1  /* diagonal storage (banded operators): no index array     */
 int amgb_hierarchy_format(const amgb_hierarchy* h, int level);
 int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level);
+/* diagonals of the level's DIA mirror (0: SELL layout).  The fused legs stream all of them, 8 bytes per
+ * row each (amgb_hierarchy_matrix_bytes excludes the 32-row slices the per-operator kernels skip). */
+int amgb_hierarchy_n_diagonals(const amgb_hierarchy* h, int level);
 
 /* algorithmic byte counts: B_l = 12 nnz_l + 28 N_l + 4 with
  * nnz_l the entries the kernels stream (explicit zeros pruned) */
