@@ -930,17 +930,7 @@ struct amgb_hierarchy {
         }
       }
       // edge chunks: those that read ghost rows (within NS + 2 lines of the block edge) or produce pushed rows
-      const int64_t lo_bound = (int64_t)lo_reach + (int64_t)(NS + 2) * P.m;
-      const int64_t hi_bound = (int64_t)hi_reach - (int64_t)(NS + 2) * P.m;
-      Y.edge_lo_chunks = 0;  // chunks whose first row lies below lo_bound
-      while (Y.edge_lo_chunks < P.n_chunks && (int64_t)P.chunk_begin(Y.edge_lo_chunks) * P.m < lo_bound) ++Y.edge_lo_chunks;
-      Y.edge_lo_chunks = std::max(Y.edge_lo_chunks, 1);
-      Y.edge_hi_chunk0 = P.n_chunks - 1;  // first chunk whose last row lies above hi_bound
-      while (Y.edge_hi_chunk0 > 0 &&
-             (int64_t)(P.chunk_begin(Y.edge_hi_chunk0 - 1) + P.chunk_lines(Y.edge_hi_chunk0 - 1)) * P.m > hi_bound)
-        --Y.edge_hi_chunk0;
-      Y.expected[0] = Y.edge_lo_chunks * P.n_strips;
-      Y.expected[1] = (P.n_chunks - Y.edge_hi_chunk0) * P.n_strips;
+      sleg::classify_edges(P, NS, lo_reach, hi_reach, Y);
     };
     for (int l = 0; l < ns; ++l) {
       wire(l, false);

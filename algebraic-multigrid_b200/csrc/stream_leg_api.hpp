@@ -129,6 +129,24 @@ struct Params {
   }
 };
 
+// Which chunks are "edge chunks" of a sharded leg (host): those that read ghost rows -- their stages
+// reach NS + 1 lines beyond the chunk -- or that produce rows / coarse entries a neighbour receives.
+// lo_reach / hi_reach: local fine rows below / from which every producer must be an edge chunk
+// (own_begin / own_end widened by the push ranges).  Fills edge_lo_chunks, edge_hi_chunk0, expected[].
+inline void classify_edges(const Params& P, int NS, int lo_reach, int hi_reach, Sync& Y) {
+  const long long lo_bound = (long long)lo_reach + (long long)(NS + 2) * P.m;
+  const long long hi_bound = (long long)hi_reach - (long long)(NS + 2) * P.m;
+  Y.edge_lo_chunks = 0;  // chunks whose first row lies below lo_bound
+  while (Y.edge_lo_chunks < P.n_chunks && (long long)P.chunk_begin(Y.edge_lo_chunks) * P.m < lo_bound) ++Y.edge_lo_chunks;
+  if (Y.edge_lo_chunks < 1) Y.edge_lo_chunks = 1;
+  Y.edge_hi_chunk0 = P.n_chunks - 1;  // first chunk whose last row lies above hi_bound
+  while (Y.edge_hi_chunk0 > 0 &&
+         (long long)(P.chunk_begin(Y.edge_hi_chunk0 - 1) + P.chunk_lines(Y.edge_hi_chunk0 - 1)) * P.m > hi_bound)
+    --Y.edge_hi_chunk0;
+  Y.expected[0] = Y.edge_lo_chunks * P.n_strips;
+  Y.expected[1] = (P.n_chunks - Y.edge_hi_chunk0) * P.n_strips;
+}
+
 __host__ __device__ constexpr int popc9(unsigned v) {
   int c = 0;
   for (int i = 0; i < 9; ++i) c += (v >> i) & 1u;
