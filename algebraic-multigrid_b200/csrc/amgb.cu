@@ -611,6 +611,10 @@ void options_default(amgb_options* o) {
   if (const char* c = std::getenv("AMGB_COMPRESS"))
     if (std::string(c) == "1") o->fuse |= 64 | 128;
   o->arith = AMGB_ARITH_REFERENCE;
+  // the C++ mirror of the reference's headers has no argument for it: AMGB_ARITH=fast selects the fast
+  // arithmetic for hierarchies created with the default options
+  if (const char* a = std::getenv("AMGB_ARITH"))
+    if (std::string(a) == "fast") o->arith = AMGB_ARITH_FAST;
 }
 
 }  // namespace
