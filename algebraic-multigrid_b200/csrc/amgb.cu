@@ -1715,7 +1715,10 @@ struct amgb_hierarchy {
       // a fused finer level does not zero u_l (its own coarse levels never read it)
       if (l > 0 && leg_ok(l - 1)) CUDA_CHECK(cudaMemsetAsync(lv[l].u.p, 0, sizeof(double) * lv[l].u.n, s));
       smooth(l, s, /*from_zero=*/l > 0);
+      const bool last_sharded = lv[l].sharded && !coarsest && !lv[l + 1].sharded;
+      if (last_sharded) mark(1, s);  // (per-operator sharded path: the gather happens inside residual_restrict)
       if (!coarsest) residual_restrict(l, s);
+      if (last_sharded) mark(2, s);
       // on the coarsest level the reference also forms the residual (:272-274);
       // it is stored in a private member without a getter and never read.
     }

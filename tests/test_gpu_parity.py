@@ -811,3 +811,26 @@ def test_dictionary_needs_few_distinct_rows():
     for _ in range(2):
         mg.vcycle(); mo.vcycle()
     assert mg.get_soln(0).tobytes() == mo.u(0).tobytes()
+
+
+def test_asymmetric_operator_device_setup():
+    """An operator that is NOT symmetric: the device-side setup must build the rows of A (transposed
+    mirror of the CSC columns) and every Galerkin level from them; damped-Jacobi cycles against the
+    oracle, which reads rows of A for Jacobi and the residual."""
+    n, L = 65, 9
+    A, b, _ = problem(n)
+    cols = np.repeat(np.arange(n * n), np.diff(A.colptr))
+    upper = A.rowidx < cols                      # entries A(r, c) with r < c
+    A.val[upper] *= 1.001                        # a small skew: the cycle still converges
+    Ao = O.Csc.from_arrays(A.rows, A.cols, A.colptr, A.rowidx, A.val)
+    sm = amg.DampedJacobi(2.0 / 3.0, 2)
+    mg = amg.Multigrid(amg.LinearInterpolator(L), sm, A, b, L, 1e-9, 1, 1)
+    mo = O.Multigrid(Ao, b, L, 1e-9, 1, 1, O.SMOOTHER_JACOBI, 2, 2.0 / 3.0)
+    for _ in range(3):
+        mg.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert mg.get_soln(l).tobytes() == mo.u(l).tobytes(), l
+        assert mg.get_rhs(l).tobytes() == mo.f(l).tobytes(), l
+    # the getters hand back the structural matrices of the host Galerkin chain
+    Ag, Aw = mg.get_coefficient_matrix(2), mo.A(2).arrays()
+    assert np.array_equal(Ag.colptr, Aw[0]) and np.array_equal(Ag.rowidx, Aw[1]) and Ag.val.tobytes() == Aw[2].tobytes()
