@@ -19,7 +19,8 @@ LIB_PATH = os.path.join(_HERE, "libamgb.so")
 
 OK, EINVAL, ECUDA, ENCCL, ESTATE = 0, 1, 2, 3, 4
 SMOOTHER_GS, SMOOTHER_JACOBI, SMOOTHER_COLOR_GS = 0, 1, 2
-GS_AUTO, GS_LEVELSCHED = 0, 1
+GS_AUTO, GS_LEVELSCHED, GS_LINESCAN = 0, 1, 2
+GS_KERNEL_FRONTS, GS_KERNEL_LINESCAN, GS_KERNEL_WAVE = 0, 1, 2
 ARITH_REFERENCE, ARITH_FAST = 0, 1
 
 _i, _l, _d, _p = C.c_int, C.c_int64, C.c_double, C.c_void_p
@@ -74,6 +75,7 @@ SIGNATURES = {
     "amgb_rss": (_i, [_p, _pd, _pd, C.POINTER(_d)]),
     "amgb_matrix_time": (_i, [_p, _i, _d, _i, _i, C.POINTER(_d)]),
     "amgb_matrix_stream_bytes": (_l, [_p, _i]),
+    "amgb_matrix_gs_kernel": (_i, [_p, _i]),
     "amgb_options_default": (None, [C.POINTER(Options)]),
     "amgb_hierarchy_create": (_i, [_i, _i, _pi, _pi, _pd, _pd, _l, C.POINTER(Options),
                                    C.POINTER(_p)]),
@@ -138,6 +140,7 @@ SIGNATURES = {
     "amgb_hierarchy_format": (_i, [_p, _i]),
     "amgb_hierarchy_matrix_bytes": (_l, [_p, _i]),
     "amgb_hierarchy_n_diagonals": (_i, [_p, _i]),
+    "amgb_hierarchy_gs_kernel": (_i, [_p, _i]),
     "amgb_time_kernel": (_i, [_p, _i, _i, _i, _i, C.POINTER(_d)]),
 }
 
@@ -316,6 +319,13 @@ class DeviceMatrix:
 
     def stream_bytes(self, kind):
         return lib().amgb_matrix_stream_bytes(self.h, kind)
+
+    def gs_kernel(self, mode=GS_AUTO):
+        """GS_KERNEL_* the lexicographic Gauss-Seidel mode runs on this matrix."""
+        k = lib().amgb_matrix_gs_kernel(self.h, mode)
+        if k < 0:
+            raise AmgbError(lib().amgb_last_error().decode())
+        return k
 
 
 def _fingerprint(A):
@@ -686,6 +696,10 @@ class Multigrid:
 
     def n_diagonals(self, level):
         return lib().amgb_hierarchy_n_diagonals(self.h, level)
+
+    def gs_kernel(self, level):
+        """GS_KERNEL_* smoothing `level` (-1 unless the smoother is SparseGaussSeidel)."""
+        return lib().amgb_hierarchy_gs_kernel(self.h, level)
 
     def pass_bytes(self, level):
         return lib().amgb_hierarchy_pass_bytes(self.h, level)

@@ -19,6 +19,7 @@
 #include "host_setup.hpp"
 #include "fused_leg.cuh"
 #include "galerkin_dia.cuh"
+#include "gs_wave.cuh"
 #include "kernels.cuh"
 #include "mid_levels.cuh"
 #include "setup_dia.cuh"
@@ -420,10 +421,134 @@ struct Operator {
     CUDA_CHECK(cudaStreamSynchronize(s));
     lines_ok = true;
   }
+  // Multi-SM wavefront Gauss-Seidel (gs_wave.cuh), bit-identical to the reference's sweep: operators
+  // whose entries couple neighbours of an n_lines x m grid and never cross the end of a line (level 0;
+  // the Galerkin levels of the 1-D interpolation do cross it and stay with the line-scan kernel).
+  bool wave_checked = false, wave_ok = false;
+  gsw::Params wave_P[2];  // [0] forward, [1] backward
+  int wave_S[2] = {0, 0};
+  unsigned wave_mask = 0;  // stencil slots in use
+  DevBuf<double> wave_coef[2], wave_hand;
+  static bool wave_enabled() {
+    static const bool on = [] {
+      const char* e = std::getenv("AMGB_GS_WAVE");
+      return !(e && std::atoi(e) == 0);
+    }();
+    return on;
+  }
+  void ensure_wave(cudaStream_t s) {
+    if (wave_checked) return;
+    wave_checked = true;
+    if (!wave_enabled() || !colrows.is_dia || block || rows_primary || n < 9) return;
+    const DevDia& D = colrows.dia;
+    if (D.rows.p || D.n_rows != n || D.n_diag > gsw::kSlots) return;
+    int cand[3];
+    gsw::plan_candidates(D.off, D.n_diag, cand);
+    DevBuf<unsigned> flags;  // [0] slots in use, [1] "an entry leaves the grid"
+    flags.alloc(2);
+    for (int ci = 0; ci < 3 && !wave_ok; ++ci) {
+      const gsw::Plan Pl = gsw::plan_for(D.off, D.n_diag, n, cand[ci]);
+      if (!Pl.ok) continue;
+      gsw::CheckArgs C{};
+      C.val = D.val.p;
+      C.ld = D.ld;
+      C.n_diag = D.n_diag;
+      C.n = n;
+      C.m = Pl.m;
+      C.n_lines = Pl.n_lines;
+      for (int d = 0; d < D.n_diag; ++d) C.e_of[d] = Pl.e_of[d];
+      flags.zero(s);
+      LAUNCH(gsw::k_gsw_check, blocks_for(n, 256), 256, 0, s, C, flags.p, reinterpret_cast<int*>(flags.p + 1));
+      unsigned got[2] = {0, 0};
+      CUDA_CHECK(cudaMemcpyAsync(got, flags.p, sizeof(got), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (got[1]) continue;
+      const int n_blocks = (Pl.n_lines + gsw::kLinesPerBlock - 1) / gsw::kLinesPerBlock;
+      gsw::Dia9 A9{};
+      A9.val = D.val.p;
+      A9.ld = D.ld;
+      for (int e = 0; e < gsw::kSlots; ++e) A9.d_of[e] = Pl.d_of[e];
+      bool fits = true;
+      for (int side = 0; side < 2; ++side) {
+        const int dir = side == 0 ? +1 : -1;
+        const int S = gsw::stride_for(got[0], dir);
+        const int T = Pl.m + S * 31;
+        const int Ts = gsw::padded_steps(T);
+        const size_t count = gsw::packed_doubles(n_blocks, T);
+        if (count * sizeof(double) > (size_t)4 << 30) {  // packed copy of the operator: keep it sane
+          fits = false;
+          break;
+        }
+        wave_coef[side].alloc(count);
+        wave_coef[side].zero(s);
+        const long long threads = (long long)n_blocks * T * gsw::kLanes;
+        LAUNCH(gsw::k_gsw_pack, (unsigned)((threads + 255) / 256), 256, 0, s, A9, n, Pl.m, Pl.n_lines, n_blocks, T, Ts,
+               S, dir, wave_coef[side].p);
+        gsw::Params P{};
+        P.n = n;
+        P.m = Pl.m;
+        P.n_lines = Pl.n_lines;
+        P.n_blocks = n_blocks;
+        P.T = T;
+        P.Ts = Ts;
+        P.coef = wave_coef[side].p;
+        P.timeout_cycles = 8000000000ll;  // ~4 s: a block whose predecessor died traps instead of hanging
+        wave_P[side] = P;
+        wave_S[side] = S;
+      }
+      if (!fits) {
+        wave_coef[0].release();
+        wave_coef[1].release();
+        break;
+      }
+      wave_mask = got[0];
+      wave_hand.alloc((size_t)n_blocks * Pl.m);
+      for (int side = 0; side < 2; ++side) wave_P[side].hand = wave_hand.p;
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      wave_ok = true;
+    }
+  }
+  void launch_wave(bool forward, const double* f, double* u, cudaStream_t s) {
+    gsw::Params P = wave_P[forward ? 0 : 1];
+    P.f = f;
+    P.u = u;
+    // the hand-over buffer starts as the sentinel (all bits set) on every sweep
+    CUDA_CHECK(cudaMemsetAsync(wave_hand.p, 0xFF, wave_hand.n * sizeof(double), s));
+    constexpr int PD = 4;  // look-ahead of the register ring in steps (covers an L2 hit; DRAM is covered by the L2 prefetches)
+    void (*kern)(gsw::Params) = nullptr;
+    const int S = wave_S[forward ? 0 : 1];
+    if ((wave_mask & ~gsw::kMaskFive) == 0)  // five-point operator: half the stencil slots compile away
+      kern = forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskFive> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskFive>;
+    else if (S == 1)
+      kern = forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskAll> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskAll>;
+    else
+      kern = forward ? gsw::k_gs_wave<2, 1, PD, gsw::kMaskAll> : gsw::k_gs_wave<2, -1, PD, gsw::kMaskAll>;
+    LAUNCH(kern, P.n_blocks, 32, 0, s, P);
+  }
+  // which kernel gs_direction runs for `mode`: 0 level-scheduled fronts, 1 line scan, 2 wavefront
+  int gs_kernel(int mode, cudaStream_t s) {
+    if (mode == AMGB_GS_AUTO) {
+      ensure_wave(s);
+      if (wave_ok) return AMGB_GS_KERNEL_WAVE;
+    }
+    if (mode == AMGB_GS_AUTO || mode == AMGB_GS_LINESCAN) {
+      ensure_lines(s);
+      if (lines_ok) return AMGB_GS_KERNEL_LINESCAN;
+    }
+    return AMGB_GS_KERNEL_FRONTS;
+  }
   // one Gauss-Seidel direction (smoother.hpp:148-157 forward, :167-174 backward)
   void gs_direction(bool forward, const double* f, double* u, double* g_scratch, int mode, cudaStream_t s) {
-    if (mode == AMGB_GS_AUTO) ensure_lines(s);
-    if (mode == AMGB_GS_AUTO && lines_ok && g_scratch) {
+    if (mode == AMGB_GS_AUTO) {
+      ensure_wave(s);
+      if (wave_ok) {
+        launch_wave(forward, f, u, s);
+        return;
+      }
+    }
+    const bool scan = mode == AMGB_GS_AUTO || mode == AMGB_GS_LINESCAN;
+    if (scan) ensure_lines(s);
+    if (scan && lines_ok && g_scratch) {
       const dev::GsLineDesc& L = line_desc[forward ? 0 : 1];
       with_view(colrows, [&](auto V) { launch_gs_rhs(V, L.dir, u, f, g_scratch, s); });
       if (lines_rows == 4) {
@@ -959,8 +1084,10 @@ struct amgb_hierarchy {
       return;
     }
     if (opt.smoother == AMGB_SMOOTHER_GS) {
-      if (opt.gs_mode == AMGB_GS_AUTO) ops[l]->ensure_lines(stream);
-      if (!(opt.gs_mode == AMGB_GS_AUTO && ops[l]->lines_ok)) ops[l]->ensure_fronts(stream);
+      const bool scan = opt.gs_mode == AMGB_GS_AUTO || opt.gs_mode == AMGB_GS_LINESCAN;
+      if (opt.gs_mode == AMGB_GS_AUTO) ops[l]->ensure_wave(stream);
+      if (scan && !ops[l]->wave_ok) ops[l]->ensure_lines(stream);
+      if (!(ops[l]->wave_ok || (scan && ops[l]->lines_ok))) ops[l]->ensure_fronts(stream);
       if (!lv[l].tmp.p) lv[l].tmp.alloc(lv[l].n_vec() + 4);
     }
     if (opt.smoother == AMGB_SMOOTHER_COLOR_GS) ops[l]->ensure_colors(stream);
@@ -2157,7 +2284,7 @@ int amgb_rss(amgb_matrix* A, const double* u, const double* b, double* out) {
 // multicolour Gauss-Seidel sweep (every colour once), 2 one residual.  CUDA events on the handle's stream.
 int amgb_matrix_time(amgb_matrix* A, int kind, double omega, int warmup, int reps, double* ms_out) {
   return guarded([&] {
-    if (!A || !ms_out || reps < 1 || kind < 0 || kind > 2) throw std::invalid_argument("bad argument");
+    if (!A || !ms_out || reps < 1 || kind < 0 || kind > 4) throw std::invalid_argument("bad argument");
     CUDA_CHECK(cudaSetDevice(A->device));
     cudaStream_t s = A->stream;
     if (A->u.n != (size_t)A->op.n || A->b.n != (size_t)A->op.n)
@@ -2171,6 +2298,8 @@ int amgb_matrix_time(amgb_matrix* A, int kind, double omega, int warmup, int rep
         std::swap(src, dst);
       } else if (kind == 1) {
         for (int c = 0; c < A->op.n_colors; ++c) A->op.color_pass(c, A->b.p, A->u.p, s);
+      } else if (kind >= 3) {
+        A->op.gs_direction(true, A->b.p, A->u.p, A->r.p, kind == 3 ? AMGB_GS_AUTO : AMGB_GS_LINESCAN, s);
       } else {
         A->op.residual(A->u.p, A->b.p, A->r.p, s);
       }
@@ -2189,6 +2318,15 @@ int amgb_matrix_time(amgb_matrix* A, int kind, double omega, int warmup, int rep
     cudaEventDestroy(e1);
     *ms_out = (double)ms / reps;
   });
+}
+int amgb_matrix_gs_kernel(amgb_matrix* A, int mode) {
+  int kind = -1;
+  const int rc = guarded([&] {
+    if (!A) throw std::invalid_argument("null argument");
+    CUDA_CHECK(cudaSetDevice(A->device));
+    kind = A->op.gs_kernel(mode, A->stream);
+  });
+  return rc == AMGB_OK ? kind : -1;
 }
 // bytes of matrix data one pass streams: kind 0 / 2 the rows-of-A mirror, kind 1 the per-colour mirrors
 int64_t amgb_matrix_stream_bytes(amgb_matrix* A, int kind) {
@@ -3256,6 +3394,13 @@ int amgb_hierarchy_n_diagonals(const amgb_hierarchy* h, int level) {
   if (!h || level < 0 || level >= h->L) return -1;
   const DevMat& A = h->ops[level]->rows_of_A();
   return A.is_dia ? A.dia.n_diag : 0;
+}
+int amgb_hierarchy_gs_kernel(const amgb_hierarchy* h, int level) {
+  if (!h || level < 0 || level >= h->L || h->opt.smoother != AMGB_SMOOTHER_GS) return -1;
+  const Operator& A = *h->ops[level];  // the schedules were built when the hierarchy was created
+  if (h->opt.gs_mode == AMGB_GS_AUTO && A.wave_ok) return AMGB_GS_KERNEL_WAVE;
+  if ((h->opt.gs_mode == AMGB_GS_AUTO || h->opt.gs_mode == AMGB_GS_LINESCAN) && A.lines_ok) return AMGB_GS_KERNEL_LINESCAN;
+  return AMGB_GS_KERNEL_FRONTS;
 }
 int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level) {
   if (!h || level < 0 || level >= h->L) return -1;

@@ -475,8 +475,10 @@ def run_b200(a):
         kern_ms = mg.time_kernel(0, 0, warmup=3, reps=20)
         bytes0 = mg.matrix_bytes(0) + 24 * (r1 - r0)       # this rank's row block
         plan = None
-        kname = {"jacobi": "k_jacobi", "color": "k_color_gs (all colours)",
-                 "gs": "k_gs_rhs + k_gs_lines (one forward direction)"}[a.smoother]
+        gs_name = ("k_gs_wave (one forward direction, multi-SM wavefront)"
+                   if a.smoother == "gs" and mg.gs_kernel(0) == amg.GS_KERNEL_WAVE
+                   else "k_gs_rhs + k_gs_lines (one forward direction)")
+        kname = {"jacobi": "k_jacobi", "color": "k_color_gs (all colours)", "gs": gs_name}[a.smoother]
         traffic_key = kname.split(" ")[0]
         kdesc = kname + " (level 0, %s layout)" % mg.format(0)
     achieved = bytes0 / (kern_ms * 1e-3) / 1e9
@@ -583,6 +585,8 @@ def run_b200(a):
                    "vcycle_hbm_frac": (layout_bytes / (ms / a.steps * 1e-3) / 1e9 / peak) if world == 1 else None,
                    "vcycle_survey_formula_bytes": vbytes,
                    "layouts": [mg.format(l) for l in range(levels)],
+                   "gs_kernels": ([{0: "fronts", 1: "linescan", 2: "wavefront"}.get(mg.gs_kernel(l)) for l in range(levels - 1)]
+                                  if a.smoother == "gs" else None),
                    "kernels_level0": per_kernel, "phases_ms": phases},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
         "gpu_launches": launches, "clocks": clocks,

@@ -44,9 +44,23 @@ extern "C" {
 #define AMGB_SMOOTHER_JACOBI 1    /* u <- u + omega D^-1 (f - A u)            */
 #define AMGB_SMOOTHER_COLOR_GS 2  /* greedy multicolour (red-black on level 0) */
 
-/* How amgb_smooth_gs orders its updates. */
-#define AMGB_GS_AUTO 0      /* fastest kernel that reproduces lexicographic order */
-#define AMGB_GS_LEVELSCHED 1 /* generic level-scheduled kernel (bit-exact)        */
+/* How amgb_smooth_gs orders its updates.  Every mode visits the rows in the reference's order
+ * (include/amg/smoother.hpp:148-174); they differ in the kernel and in whether its arithmetic is
+ * the reference's bit for bit.
+ *   AUTO        grid-structured operators (every entry couples neighbours of an n_lines x m grid and
+ *               none crosses the end of a line: level 0) run the multi-SM wavefront kernel, bit-exact;
+ *               other banded operators (the Galerkin levels, whose 1-D interpolation couples across
+ *               line ends) the line-scan kernel; anything else the level-scheduled kernel.
+ *   LEVELSCHED  generic level-scheduled kernel, one SM, bit-exact.
+ *   LINESCAN    single-SM affine-scan kernel (re-associates the distance-1 chain: <= 1e-14 relative),
+ *               level-scheduled kernel where it does not apply. */
+#define AMGB_GS_AUTO 0
+#define AMGB_GS_LEVELSCHED 1
+#define AMGB_GS_LINESCAN 2
+/* kernels behind the modes (amgb_matrix_gs_kernel) */
+#define AMGB_GS_KERNEL_FRONTS 0
+#define AMGB_GS_KERNEL_LINESCAN 1
+#define AMGB_GS_KERNEL_WAVE 2
 
 typedef struct amgb_matrix amgb_matrix;       /* device mirror of one CSC matrix */
 typedef struct amgb_hierarchy amgb_hierarchy; /* device mirror of AMG::Multigrid  */
@@ -130,10 +144,14 @@ int amgb_rss(amgb_matrix* A, const double* u, const double* b, double* out);
 /* Timing hook of the smoother + residual microbenchmark: mean milliseconds
  * per launch (CUDA events on the handle's stream) of one pass over the matrix on the vectors the
  * last amgb_residual / amgb_rss call uploaded.  kind 0: one damped-Jacobi sweep, 1: one
- * colour-complete multicolour Gauss-Seidel sweep, 2: one residual.  amgb_matrix_stream_bytes: the
+ * colour-complete multicolour Gauss-Seidel sweep, 2: one residual (3, 4: below).  amgb_matrix_stream_bytes: the
  * matrix bytes such a pass streams (kind 1 after the colouring exists). */
 int amgb_matrix_time(amgb_matrix* A, int kind, double omega, int warmup, int reps, double* ms_per_launch);
 int64_t amgb_matrix_stream_bytes(amgb_matrix* A, int kind);
+/* kind 3 / 4 of amgb_matrix_time: one FORWARD lexicographic Gauss-Seidel sweep (in place on the uploaded
+ * u) with AMGB_GS_AUTO / AMGB_GS_LINESCAN.  amgb_matrix_gs_kernel: the AMGB_GS_KERNEL_* that `mode`
+ * selects for this matrix (builds the kernel's schedule if it does not exist yet); -1 on error. */
+int amgb_matrix_gs_kernel(amgb_matrix* A, int mode);
 
 /* ------------------------------------------------------------------------
  * Hierarchy = AMG::Multigrid<double> (include/amg/multigrid.hpp:22-365).
@@ -356,6 +374,8 @@ int64_t amgb_hierarchy_matrix_bytes(const amgb_hierarchy* h, int level);
 /* diagonals of the level's DIA mirror (0: SELL layout).  The fused legs stream all of them, 8 bytes per
  * row each (amgb_hierarchy_matrix_bytes excludes the 32-row slices the per-operator kernels skip). */
 int amgb_hierarchy_n_diagonals(const amgb_hierarchy* h, int level);
+/* AMGB_GS_KERNEL_* that smooths `level` of a Gauss-Seidel hierarchy (-1: not a Gauss-Seidel hierarchy) */
+int amgb_hierarchy_gs_kernel(const amgb_hierarchy* h, int level);
 
 /* algorithmic byte counts: B_l = 12 nnz_l + 28 N_l + 4 with
  * nnz_l the entries the kernels stream (explicit zeros pruned) */

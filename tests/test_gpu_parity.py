@@ -98,18 +98,86 @@ def test_gauss_seidel_levelsched_bit_exact(n, eps):
 
 @pytest.mark.parametrize("n,eps", [(2, 1.0), (3, 1.0), (35, 1.0), (64, 1.0), (33, 1e-3), (200, 1.0), (513, 1.0)])
 def test_gauss_seidel_linescan(n, eps):
-    """Banded line-scan kernel (default mode): same update order, the distance-1 chain is a
-    parallel scan, so agreement is to rounding rather than bit for bit."""
+    """Banded line-scan kernel: same update order, the distance-1 chain is a parallel scan, so
+    agreement is to rounding rather than bit for bit."""
     A, b, Ao = problem(n, eps)
+    u = vec(n * n, 5)
+    want = u.copy()
+    O.gs_smooth(Ao, want, b, 1e-9, 0, 3)
+    got = u.copy()
+    sm = amg.SparseGaussSeidel(mode=amg.GS_LINESCAN)
+    sm.n_iters = 3
+    sm.smooth(A, got, b)
+    assert rel(got, want) <= 1e-14
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n,eps", [(3, 1.0), (4, 1.0), (31, 1.0), (35, 1.0), (64, 1.0), (33, 1e-3), (100, 1.0),
+                                   (257, 1e-2), (513, 1.0)])
+def test_gauss_seidel_wavefront_bit_exact(n, eps):
+    """Default mode on a grid operator (level 0): the multi-SM wavefront kernel (gs_wave.cuh) -- one to 18
+    blocks of 30 grid lines chained through the hand-over buffer -- reproduces the reference's sweeps
+    (smoother.hpp:148-174) bit for bit, forward and backward, several iterations."""
+    A, b, Ao = problem(n, eps)
+    dm = amg.DeviceMatrix(A)
+    assert dm.gs_kernel(amg.GS_AUTO) == amg.GS_KERNEL_WAVE
+    assert dm.gs_kernel(amg.GS_LINESCAN) == amg.GS_KERNEL_LINESCAN
+    assert dm.gs_kernel(amg.GS_LEVELSCHED) == amg.GS_KERNEL_FRONTS
     u = vec(n * n, 5)
     want = u.copy()
     O.gs_smooth(Ao, want, b, 1e-9, 0, 3)
     got = u.copy()
     sm = amg.SparseGaussSeidel()
     sm.n_iters = 3
-    sm.smooth(A, got, b)
-    assert rel(got, want) <= 1e-14
-    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+    sm.smooth(dm, got, b)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_gauss_seidel_wavefront_unsymmetric_and_pruned():
+    """The wavefront kernel on an operator that is not symmetric and has pruned entries and a zero
+    diagonal entry (that row is left alone, smoother.hpp:136): still the reference's bits.  The sweep
+    works on "row c = CSC column c", so the oracle gets the very same CSC arrays."""
+    n = 48
+    A, b, _ = problem(n)
+    rng = np.random.default_rng(11)
+    cols = np.repeat(np.arange(n * n), np.diff(A.colptr))
+    off = A.rowidx != cols
+    A.val[off] *= 0.5 + rng.random(int(off.sum()))           # unsymmetric
+    A.val[off & (rng.random(A.val.size) < 0.05)] = 0.0       # stored zeros: pruned from the mirror
+    A.val[np.flatnonzero(~off)[777]] = 0.0                   # one zero diagonal entry
+    Ao = O.Csc.from_arrays(A.rows, A.cols, A.colptr, A.rowidx, A.val)
+    dm = amg.DeviceMatrix(A)
+    assert dm.gs_kernel(amg.GS_AUTO) == amg.GS_KERNEL_WAVE
+    u = vec(n * n, 9)
+    want = u.copy()
+    O.gs_smooth(Ao, want, b, 1e-9, 0, 2)
+    got = u.copy()
+    sm = amg.SparseGaussSeidel()
+    sm.n_iters = 2
+    sm.smooth(dm, got, b)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_galerkin_levels_keep_the_scan_kernel():
+    """The Galerkin operators couple across the ends of grid lines (1-D interpolation of the flattened
+    vector): AUTO must not pick the wavefront kernel for them."""
+    mo = O.Multigrid(O.laplacian(65), O.rhs(65), 4, 1e-9, 1, 1)
+    for l in (1, 2, 3):
+        Al = mo.A(l)
+        c, r, v = Al.arrays()
+        dm = amg.DeviceMatrix(amg.CscMatrix(Al.rows, Al.cols, c, r, v))
+        assert dm.gs_kernel(amg.GS_AUTO) == amg.GS_KERNEL_LINESCAN, l
+
+
+def test_vcycle_gs_level0_wavefront_matches_oracle():
+    """V-cycles with the default Gauss-Seidel mode (wavefront kernel on level 0, scan kernel below) stay
+    within rounding of the oracle on every level."""
+    n, L = 129, 10
+    mg, mo, _ = make_pair(n, L, amg.SparseGaussSeidel())
+    for _ in range(3):
+        mg.vcycle(); mo.vcycle()
+    for l in range(L):
+        assert rel(mg.get_soln(l), mo.u(l)) <= 1e-12, l
 
 
 @pytest.mark.parametrize("n,L,eps", [(65, 9, 1.0), (129, 11, 1e-3), (257, 10, 1.0)])
@@ -265,7 +333,8 @@ def test_coarse_solve_every_bandwidth(n, L):
 
 SMOOTHERS = [
     ("gs", lambda: amg.SparseGaussSeidel(mode=amg.GS_LEVELSCHED)),
-    ("gs_linescan", lambda: amg.SparseGaussSeidel()),
+    ("gs_linescan", lambda: amg.SparseGaussSeidel(mode=amg.GS_LINESCAN)),
+    ("gs_auto", lambda: amg.SparseGaussSeidel()),
     ("jacobi", lambda: amg.DampedJacobi(2.0 / 3.0, 2)),
     ("color", lambda: amg.MulticolorGaussSeidel(1)),
 ]
@@ -285,7 +354,7 @@ def test_vcycle_per_level_iterates(name, mk, n, L, eps):
             if l + 1 < L or True:
                 assert rel(mg.get_rhs(l), mo.f(l)) <= RTOL or not mo.f(l).any()
     # these kernels keep the oracle's operation order: expect identical bits on the fine level
-    if name != "gs_linescan":
+    if name not in ("gs_linescan", "gs_auto"):   # (gs_auto: the scan kernel still smooths the Galerkin levels)
         assert mg.get_soln(0).tobytes() == mo.u(0).tobytes()
 
 
@@ -326,7 +395,7 @@ def test_amg_solve_golden(capsys, mode):
     assert np.dot(d, d) <= 1e-12 * min(np.dot(amg_u, amg_u), np.dot(spgs_u, spgs_u))  # :212
 
 
-@pytest.mark.parametrize("name,mk", SMOOTHERS[2:])
+@pytest.mark.parametrize("name,mk", SMOOTHERS[3:])
 def test_solve_iteration_counts_match_oracle(name, mk):
     mg, mo, _ = make_pair(35, 8, mk(), every=5, n_iters=400)
     mg.solve()
