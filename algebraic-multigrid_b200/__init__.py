@@ -76,6 +76,7 @@ SIGNATURES = {
     "amgb_matrix_time": (_i, [_p, _i, _d, _i, _i, C.POINTER(_d)]),
     "amgb_matrix_stream_bytes": (_l, [_p, _i]),
     "amgb_matrix_gs_kernel": (_i, [_p, _i]),
+    "amgb_selftest_division": (_i, [_l, C.c_uint64, C.POINTER(_l)]),
     "amgb_options_default": (None, [C.POINTER(Options)]),
     "amgb_hierarchy_create": (_i, [_i, _i, _pi, _pi, _pd, _pd, _l, C.POINTER(Options),
                                    C.POINTER(_p)]),
@@ -363,6 +364,13 @@ def _mirror(A):
         cached = (fp, DeviceMatrix(A))
         A._amgb_mirror = cached
     return cached[1]
+
+
+def selftest_division(n_pairs=1 << 24, seed=1):
+    """Mismatches between the wavefront kernel's split division and the compiler's IEEE division."""
+    bad = _l()
+    _check(lib().amgb_selftest_division(n_pairs, seed, C.byref(bad)))
+    return bad.value
 
 
 def rss(A, u, b):

@@ -508,21 +508,30 @@ struct Operator {
       wave_ok = true;
     }
   }
+  // AMGB_GS_WAVE_DIV=exact: __ddiv_rn inside the sweep; default: the split form of the same division
+  // (gs_wave.cuh div_split), whose reciprocal part is evaluated when the operator is packed
+  static bool wave_split_division() {
+    const char* e = std::getenv("AMGB_GS_WAVE_DIV");
+    return !(e && std::strcmp(e, "exact") == 0);
+  }
+  template <bool SPLIT>
+  static void (*pick_wave(bool five, int S, bool forward))(gsw::Params) {
+    constexpr int PD = 4;  // look-ahead of the register ring in steps (covers an L2 hit; DRAM is covered by the L2 prefetches)
+    if (five) return forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskFive, SPLIT> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskFive, SPLIT>;
+    if (S == 1) return forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskAll, SPLIT> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskAll, SPLIT>;
+    return forward ? gsw::k_gs_wave<2, 1, PD, gsw::kMaskAll, SPLIT> : gsw::k_gs_wave<2, -1, PD, gsw::kMaskAll, SPLIT>;
+  }
   void launch_wave(bool forward, const double* f, double* u, cudaStream_t s) {
     gsw::Params P = wave_P[forward ? 0 : 1];
     P.f = f;
     P.u = u;
     // the hand-over buffer starts as the sentinel (all bits set) on every sweep
     CUDA_CHECK(cudaMemsetAsync(wave_hand.p, 0xFF, wave_hand.n * sizeof(double), s));
-    constexpr int PD = 4;  // look-ahead of the register ring in steps (covers an L2 hit; DRAM is covered by the L2 prefetches)
     void (*kern)(gsw::Params) = nullptr;
     const int S = wave_S[forward ? 0 : 1];
-    if ((wave_mask & ~gsw::kMaskFive) == 0)  // five-point operator: half the stencil slots compile away
-      kern = forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskFive> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskFive>;
-    else if (S == 1)
-      kern = forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskAll> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskAll>;
-    else
-      kern = forward ? gsw::k_gs_wave<2, 1, PD, gsw::kMaskAll> : gsw::k_gs_wave<2, -1, PD, gsw::kMaskAll>;
+    const bool five = (wave_mask & ~gsw::kMaskFive) == 0;  // five-point operator: half the stencil slots compile away
+    if (wave_split_division()) kern = pick_wave<true>(five, S, forward);
+    else kern = pick_wave<false>(five, S, forward);
     LAUNCH(kern, P.n_blocks, 32, 0, s, P);
   }
   // which kernel gs_direction runs for `mode`: 0 level-scheduled fronts, 1 line scan, 2 wavefront
@@ -2317,6 +2326,18 @@ int amgb_matrix_time(amgb_matrix* A, int kind, double omega, int warmup, int rep
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_out = (double)ms / reps;
+  });
+}
+int amgb_selftest_division(int64_t n_pairs, uint64_t seed, int64_t* mismatches) {
+  return guarded([&] {
+    if (!mismatches || n_pairs < 0) throw std::invalid_argument("bad argument");
+    DevBuf<unsigned long long> count;
+    count.alloc(1);
+    count.zero(nullptr);
+    LAUNCH(gsw::k_gsw_division_selftest, 1184, 256, 0, nullptr, (long long)n_pairs, (unsigned long long)seed, count.p);
+    unsigned long long got = 0;
+    CUDA_CHECK(cudaMemcpy(&got, count.p, sizeof(got), cudaMemcpyDeviceToHost));
+    *mismatches = (int64_t)got;
   });
 }
 int amgb_matrix_gs_kernel(amgb_matrix* A, int mode) {

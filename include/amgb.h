@@ -152,6 +152,11 @@ int64_t amgb_matrix_stream_bytes(amgb_matrix* A, int kind);
  * u) with AMGB_GS_AUTO / AMGB_GS_LINESCAN.  amgb_matrix_gs_kernel: the AMGB_GS_KERNEL_* that `mode`
  * selects for this matrix (builds the kernel's schedule if it does not exist yet); -1 on error. */
 int amgb_matrix_gs_kernel(amgb_matrix* A, int mode);
+/* Diagnostic: the wavefront kernel evaluates (b_i - sigma) / a_ii as the split form of the compiler's
+ * IEEE division (reciprocal refinement at pack time, three dependent operations per row, the
+ * compiler's own range guard and fallback).  This runs both forms on n_pairs pseudo-random operand
+ * pairs on the current device and counts results whose bits differ (must be 0). */
+int amgb_selftest_division(int64_t n_pairs, uint64_t seed, int64_t* mismatches);
 
 /* ------------------------------------------------------------------------
  * Hierarchy = AMG::Multigrid<double> (include/amg/multigrid.hpp:22-365).

@@ -39,7 +39,7 @@ struct Emu {
   In load(int b, int j, int tt) const {
     In in{};
     for (int e = 0; e < kSlots; ++e)
-      in.c[e] = ((MASK >> e) & 1u) ? coef[(((size_t)b * G.Ts + tt) * kSlots + e) * kLanes + j] : 0.0;
+      in.c[e] = ((MASK >> e) & 1u) ? coef[(((size_t)b * G.Ts + tt) * kPacked + e) * kLanes + j] : 0.0;
     const int Y = line_of(b, j), X = tt - S * j;
     const int Yc = Y < 0 ? 0 : (Y >= G.n_lines ? G.n_lines - 1 : Y);
     auto clampx = [&](int x) { return x < 0 ? 0 : (x >= G.m ? G.m - 1 : x); };
@@ -188,7 +188,7 @@ int gsw_host_sweep(int n, int n_diag, const int* off, int ld, const double* val,
       for (int t = 0; t < G.T; ++t)
         for (int e = 0; e < kSlots; ++e)
           for (int j = 0; j < kLanes; ++j)
-            coef[(((size_t)b * G.Ts + t) * kSlots + e) * kLanes + j] =
+            coef[(((size_t)b * G.Ts + t) * kPacked + e) * kLanes + j] =
                 packed_coef(A, n, P.m, P.n_lines, G.S, dir, b, t, j, e);
     if (S_out) *S_out = G.S;
     if (m_out) *m_out = P.m;

@@ -133,6 +133,30 @@ def test_gauss_seidel_wavefront_bit_exact(n, eps):
     assert got.tobytes() == want.tobytes()
 
 
+def test_wavefront_split_division_is_the_ieee_division():
+    """The wavefront kernel evaluates (b - sigma) / a_ii in the split form of the compiler's division;
+    the device self-test compares it with __ddiv_rn on 2^25 operand pairs (every 16th pair with
+    exponents over the whole range, denormals and specials included): not one bit may differ."""
+    assert amg.selftest_division(1 << 25, seed=12345) == 0
+    assert amg.selftest_division(1 << 22, seed=7) == 0
+
+
+@pytest.mark.parametrize("div", ["split", "exact"])
+def test_gauss_seidel_wavefront_division_variants(div, monkeypatch):
+    """Both division variants of the wavefront kernel give the oracle's bits (AMGB_GS_WAVE_DIV)."""
+    monkeypatch.setenv("AMGB_GS_WAVE_DIV", div)
+    n = 70
+    A, b, Ao = problem(n, 1e-1)
+    u = vec(n * n, 21)
+    want = u.copy()
+    O.gs_smooth(Ao, want, b, 1e-9, 0, 2)
+    got = u.copy()
+    sm = amg.SparseGaussSeidel()
+    sm.n_iters = 2
+    sm.smooth(amg.DeviceMatrix(A), got, b)
+    assert got.tobytes() == want.tobytes()
+
+
 def test_gauss_seidel_wavefront_unsymmetric_and_pruned():
     """The wavefront kernel on an operator that is not symmetric and has pruned entries and a zero
     diagonal entry (that row is left alone, smoother.hpp:136): still the reference's bits.  The sweep
