@@ -516,7 +516,9 @@ struct Operator {
   }
   template <bool SPLIT>
   static void (*pick_wave(bool five, int S, bool forward))(gsw::Params) {
-    constexpr int PD = 4;  // look-ahead of the register ring in steps (covers an L2 hit; DRAM is covered by the L2 prefetches)
+    // look-ahead of the register ring in steps (covers an L2 hit; DRAM is covered by the L2 prefetches).
+    // PD + 1 = 6 is a multiple of the three-deep neighbour histories, so the unrolled loop carries no moves.
+    constexpr int PD = 5;
     if (five) return forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskFive, SPLIT> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskFive, SPLIT>;
     if (S == 1) return forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskAll, SPLIT> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskAll, SPLIT>;
     return forward ? gsw::k_gs_wave<2, 1, PD, gsw::kMaskAll, SPLIT> : gsw::k_gs_wave<2, -1, PD, gsw::kMaskAll, SPLIT>;
