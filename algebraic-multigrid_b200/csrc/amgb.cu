@@ -514,11 +514,15 @@ struct Operator {
     const char* e = std::getenv("AMGB_GS_WAVE_DIV");
     return !(e && std::strcmp(e, "exact") == 0);
   }
-  template <bool SPLIT>
+  // look-ahead of the register ring in steps.  PD + 1 is a multiple of the three-deep neighbour
+  // histories (the unrolled loop carries no moves); 5 steps cover an L2 miss of the per-lane f / u
+  // lines, 2 steps (AMGB_GS_WAVE_PD=2) keep fewer loads in flight per scoreboard.
+  static int wave_lookahead() {
+    const char* e = std::getenv("AMGB_GS_WAVE_PD");
+    return (e && std::atoi(e) == 2) ? 2 : 5;
+  }
+  template <bool SPLIT, int PD>
   static void (*pick_wave(bool five, int S, bool forward))(gsw::Params) {
-    // look-ahead of the register ring in steps (covers an L2 hit; DRAM is covered by the L2 prefetches).
-    // PD + 1 = 6 is a multiple of the three-deep neighbour histories, so the unrolled loop carries no moves.
-    constexpr int PD = 5;
     if (five) return forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskFive, SPLIT> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskFive, SPLIT>;
     if (S == 1) return forward ? gsw::k_gs_wave<1, 1, PD, gsw::kMaskAll, SPLIT> : gsw::k_gs_wave<1, -1, PD, gsw::kMaskAll, SPLIT>;
     return forward ? gsw::k_gs_wave<2, 1, PD, gsw::kMaskAll, SPLIT> : gsw::k_gs_wave<2, -1, PD, gsw::kMaskAll, SPLIT>;
@@ -532,8 +536,9 @@ struct Operator {
     void (*kern)(gsw::Params) = nullptr;
     const int S = wave_S[forward ? 0 : 1];
     const bool five = (wave_mask & ~gsw::kMaskFive) == 0;  // five-point operator: half the stencil slots compile away
-    if (wave_split_division()) kern = pick_wave<true>(five, S, forward);
-    else kern = pick_wave<false>(five, S, forward);
+    const bool split = wave_split_division();
+    if (wave_lookahead() == 2) kern = split ? pick_wave<true, 2>(five, S, forward) : pick_wave<false, 2>(five, S, forward);
+    else kern = split ? pick_wave<true, 5>(five, S, forward) : pick_wave<false, 5>(five, S, forward);
     LAUNCH(kern, P.n_blocks, 32, 0, s, P);
   }
   // which kernel gs_direction runs for `mode`: 0 level-scheduled fronts, 1 line scan, 2 wavefront

@@ -41,6 +41,12 @@ for shape in (sys.argv[1:] or ["30x1025", "60x1025", "1025x1025", "2049x2049"]):
         if div == "exact":
             amg.rss(dm, u, b)
             out["linescan_ms"] = dm.time_pass(4, warmup=3, reps=10)
+    os.environ["AMGB_GS_WAVE_DIV"] = "split"
+    os.environ["AMGB_GS_WAVE_PD"] = "2"
+    dm = amg.DeviceMatrix(A)
+    amg.rss(dm, u, b)
+    out["wave_split_pd2_ms"] = dm.time_pass(3, warmup=3, reps=10)
+    os.environ["AMGB_GS_WAVE_PD"] = "5"
     blocks = (n_lines + 29) // 30
     steps = m + 31
     out.update(wave_blocks=blocks, wave_steps_per_block=steps,

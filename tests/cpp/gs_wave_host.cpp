@@ -29,7 +29,7 @@ struct Emu {
   std::vector<double> hand;
   struct Block {
     int t = 0;
-    bool loaded = false;  // the loads of step t + PD were issued before the block started to wait
+    bool loaded = false;  // the inputs of step t have been taken out of the ring
     std::vector<Lane<S>> L;
     std::vector<In> ring;  // [lane * pd + r]
     std::vector<In> cur;   // inputs of the step in flight
@@ -64,16 +64,12 @@ struct Emu {
     }
   }
   int t_end() const { return (G.T + G.pd) / (G.pd + 1) * (G.pd + 1); }
-  // one step of block b; false: the block has to wait (nothing but its look-ahead loads happened)
+  // one step of block b; false: the block has to wait (nothing happened)
   bool step(int b) {
     Block& B = blocks[b];
     const int t = B.t;
     if (!B.loaded) {
-      for (int j = 0; j < kLanes; ++j) {
-        In& slot = B.ring[(size_t)j * G.pd + t % G.pd];
-        B.cur[j] = slot;
-        slot = load(b, j, t + G.pd);
-      }
+      for (int j = 0; j < kLanes; ++j) B.cur[j] = B.ring[(size_t)j * G.pd + t % G.pd];
       B.loaded = true;
     }
     if (b > 0 && t < G.m) {  // lane 0 is inside its line for t < m
@@ -101,6 +97,8 @@ struct Emu {
       }
       B.L[j].out = out;
     }
+    // like the kernel: the look-ahead loads of step t + PD are issued at the END of step t
+    for (int j = 0; j < kLanes; ++j) B.ring[(size_t)j * G.pd + t % G.pd] = load(b, j, t + G.pd);
     B.t += 1;
     B.loaded = false;
     return true;

@@ -141,10 +141,12 @@ def test_wavefront_split_division_is_the_ieee_division():
     assert amg.selftest_division(1 << 22, seed=7) == 0
 
 
-@pytest.mark.parametrize("div", ["split", "exact"])
-def test_gauss_seidel_wavefront_division_variants(div, monkeypatch):
-    """Both division variants of the wavefront kernel give the oracle's bits (AMGB_GS_WAVE_DIV)."""
+@pytest.mark.parametrize("div,pd", [("split", "5"), ("exact", "5"), ("split", "2"), ("exact", "2")])
+def test_gauss_seidel_wavefront_division_variants(div, pd, monkeypatch):
+    """Both division variants and both look-ahead depths of the wavefront kernel give the oracle's bits
+    (AMGB_GS_WAVE_DIV, AMGB_GS_WAVE_PD)."""
     monkeypatch.setenv("AMGB_GS_WAVE_DIV", div)
+    monkeypatch.setenv("AMGB_GS_WAVE_PD", pd)
     n = 70
     A, b, Ao = problem(n, 1e-1)
     u = vec(n * n, 21)
